@@ -1,0 +1,181 @@
+"""The CPU oracle (oracle/) pinned against outputs of the reference itself
+(tests/golden/*.npz, made by tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from conftest import load_golden
+
+HAM_CASES = ["lih", "beh2", "n2", "ragged", "sparse", "edge_full_alpha", "edge_no_beta", "wide"]
+
+
+def ham_of(g):
+    n_orb, na, nb = (int(x) for x in g["shape"])
+    return orc.OracleHam(g["h1"], g["g"], na, nb, float(g.get("e_nuc", 0.0)))
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_connections_emission_order_and_values(name):
+    g = load_golden("ham_" + name)
+    H = ham_of(g)
+    offs = g["conn_offsets"]
+    for j, det in enumerate(g["dets"]):
+        c, e = H.connections(det)
+        ref_c = g["conn_cfgs"][offs[j]:offs[j + 1]]
+        ref_e = g["conn_elems"][offs[j]:offs[j + 1]]
+        assert c.shape == ref_c.shape
+        assert np.array_equal(c, ref_c)                 # same dets, same order
+        assert np.array_equal(e.view(np.uint32), ref_e.view(np.uint32))   # bit-exact float32
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_batch_matches_single(name):
+    g = load_golden("ham_" + name)
+    H = ham_of(g)
+    c, e, src, offs = H.connections_batch(g["dets"])
+    assert np.array_equal(offs, g["conn_offsets"])
+    assert np.array_equal(c, g["conn_cfgs"])
+    assert np.array_equal(e.view(np.uint32), g["conn_elems"].view(np.uint32))
+    assert np.array_equal(src, np.repeat(np.arange(len(g["dets"])), np.diff(offs)))
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_diag_fp64_within_float32_envelope(name):
+    g = load_golden("ham_" + name)
+    H = ham_of(g)
+    d = H.diag(g["dets"])
+    # the reference diagonal is a float32 einsum: agreement is float32-limited
+    scale = max(1.0, float(np.abs(d).max()))
+    assert np.abs(d - g["diag32"].astype(np.float64)).max() < 2e-5 * scale
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_projected_h_offdiag_bit_exact(name):
+    g = load_golden("ham_" + name)
+    H = ham_of(g)
+    r, c, v = H.offdiag_coo(g["basis"])
+    assert np.array_equal(r, g["coo_rows"])
+    assert np.array_equal(c, g["coo_cols"])
+    assert np.array_equal(v.view(np.uint32), g["coo_vals"].astype(np.float32).view(np.uint32))
+    D = H.dense_H(g["basis"])
+    ref = g["H_dense32"].astype(np.float64)
+    off = ~np.eye(len(D), dtype=bool)
+    assert np.array_equal(D[off], ref[off])             # pattern + values, bit-exact
+    assert np.abs(np.diag(D) - np.diag(ref)).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_sign_double_antisymmetry_quirk_F3():
+    """molecular.py:391-423 is not antisymmetry-consistent: some same-spin
+    doubles have H[i,j] = -H[j,i].  The oracle must reproduce it."""
+    g = load_golden("skqd_lih")
+    H = ham_of(g)
+    D = H.dense_H(g["subspace"])
+    off = D - np.diag(np.diag(D))
+    anti = np.abs(off + off.T) < 1e-30
+    sym = np.abs(off - off.T) < 1e-30
+    nz = np.abs(off) > 0
+    assert (anti & nz).sum() > 0 and (sym & nz).sum() > 0
+    assert ((anti | sym) | ~nz).all()
+
+
+@pytest.mark.parametrize("name", ["lih", "beh2"])
+def test_fci_energy(name):
+    g = load_golden("fci_" + name)
+    H = ham_of(g)
+    E, _ = H.diagonalize(H.fci_basis())
+    assert abs(E - float(g["fci"])) < 5e-6          # float32 diagonal envelope
+
+
+@pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide"])
+def test_selected_ci_rounds(name):
+    g = load_golden("sci_" + name)
+    H = ham_of(g)
+    k = int(g["k"])
+    basis = g["basis0"]
+    for rd in range(int(g["rounds"])):
+        # selection on the REFERENCE's own eigenpair: candidates + importances
+        sel, imp, cand, imp_all, _ = H.find_important_configs(
+            basis, float(g[f"r{rd}_E"]), g[f"r{rd}_v"], k, precision="f32")
+        ref_sel, ref_imp = g[f"r{rd}_sel"], g[f"r{rd}_imp"]
+        assert len(sel) == len(ref_sel)
+        # same selected SET unless a near-tie sits at the cut (epsilon band)
+        got = {bytes(r) for r in sel}
+        want = {bytes(r) for r in ref_sel}
+        if got != want:
+            cut = float(ref_imp.min())
+            for r in got ^ want:
+                i = [bytes(x) for x in cand].index(r)
+                assert abs(imp_all[i] - cut) <= 1e-5 * cut
+        srt = np.sort(ref_imp.astype(np.float64))[::-1]
+        assert np.allclose(np.sort(imp.astype(np.float64))[::-1], srt, rtol=2e-4, atol=1e-12)
+        # full round through the oracle's own numerics
+        new_basis, st = H.expand_basis(basis, k)
+        assert np.array_equal(new_basis, g[f"r{rd}_basis"])
+        assert abs(st["final_energy"] - float(g[f"r{rd}_final_energy"])) < 5e-6
+        basis = new_basis
+
+
+def test_skqd_subspace_csr_and_time_evolution():
+    for name in ("lih", "h5"):
+        g = load_golden("skqd_" + name)
+        H = ham_of(g)
+        sub = H.fci_basis()
+        assert np.array_equal(sub, g["subspace"])
+        M = H.raw_csr(sub)
+        assert np.array_equal(M.indptr, g["H_indptr"])
+        assert np.array_equal(M.indices, g["H_indices"])
+        ref = g["H_data"]
+        isdiag = M.indices == np.repeat(np.arange(len(sub)), np.diff(M.indptr))
+        assert np.array_equal(M.data[~isdiag], ref[~isdiag])
+        assert np.abs(M.data[isdiag] - ref[isdiag]).max() < 2e-5
+        # time evolution on the REFERENCE's matrix: Taylor vs scipy expm_multiply
+        psi = np.zeros(len(sub), np.complex128)
+        psi[int(g["hf_index"])] = 1.0
+        for step in range(3):
+            psi = orc.expm_multiply_taylor(g["H_indptr"], g["H_indices"], ref, psi, 0.1)
+            assert np.abs(psi - g["psi_steps"][step]).max() < 1e-12
+
+
+def test_ground_state_energy_quirk_F5():
+    g = load_golden("skqd_lih")
+    H = ham_of(g)
+    for tag in ("big", "small"):
+        b = g[f"gse_{tag}_basis"]
+        e_vec, v = H.ground_state_energy(b, True)
+        e_no, _ = H.ground_state_energy(b, False)
+        assert abs(e_vec - float(g[f"gse_{tag}_E_vec"])) < 5e-6
+        assert abs(e_no - float(g[f"gse_{tag}_E_novec"])) < 5e-6
+        ov = abs(np.dot(v, g[f"gse_{tag}_v"]))
+        assert ov > 1 - 1e-6
+    assert float(g["gse_big_E_novec"]) > float(g["gse_big_E_vec"]) + 1e-3   # lambda_1, not lambda_0
+
+
+def test_skqd_energies_on_reference_samples():
+    g = load_golden("skqd_lih")
+    H = ham_of(g)
+    nf = g["nf_basis"]
+    e_nf, _ = H.ground_state_energy(nf, False)
+    assert abs(e_nf - float(g["energy_nf_only"])) < 5e-6
+    for k in range(1, int(g["kdim"])):
+        kb = g[f"krylov_basis_{k}"]
+        comb = orc.sort_unique(np.concatenate([nf, kb]))
+        assert len(kb) == int(g["basis_sizes_krylov"][k - 1])
+        assert len(comb) == int(g["basis_sizes_combined"][k - 1])
+        e_k, _ = H.ground_state_energy(kb, False)
+        e_c, _ = H.ground_state_energy(comb, False)
+        assert abs(e_k - float(g["energies_krylov"][k - 1])) < 5e-6
+        assert abs(e_c - float(g["energies_combined"][k - 1])) < 5e-6
+
+
+def test_spmv_oracle_vs_numpy():
+    g = load_golden("skqd_lih")
+    rng = np.random.default_rng(0)
+    n = len(g["H_indptr"]) - 1
+    import scipy.sparse as sp
+    M = sp.csr_matrix((g["H_data"], g["H_indices"], g["H_indptr"]), shape=(n, n))
+    x = rng.standard_normal(n)
+    assert np.allclose(orc.csr_matvec(g["H_indptr"], g["H_indices"], g["H_data"], x), M @ x,
+                       rtol=0, atol=1e-12)
+    z = x + 1j * rng.standard_normal(n)
+    assert np.allclose(orc.csr_matvec(g["H_indptr"], g["H_indices"], g["H_data"], z), M @ z,
+                       rtol=0, atol=1e-12)
