@@ -1,0 +1,335 @@
+// fgk_core.cuh -- bit-level determinant algebra shared by every kernel.
+//
+// Everything here is __host__ __device__ so that the exact same arithmetic the
+// kernels run can be compiled by g++ into a CPU self-check (csrc/fgk_hostcheck.cpp,
+// used by the "not gpu" tests) and compared with the oracle without a GPU.
+//
+// Conventions (DESIGN.md "Data layout"):
+//   * a determinant is two 64-bit occupation words {alpha, beta};
+//   * orbital p of a spin block lives in bit (n_orb-1-p), so that the pair
+//     (alpha, beta) compared as a 128-bit unsigned number orders determinants
+//     exactly like the reference's site-0-is-MSB integer key
+//     (reference molecular.py:498-500, torch.unique order);
+//   * "site" = orbital for alpha, n_orb + orbital for beta (molecular.py:43-45).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FGK_HD __host__ __device__ __forceinline__
+#else
+#define FGK_HD inline
+#endif
+
+typedef unsigned long long u64;
+
+struct fgk_det { u64 a, b; };   // 16 B, loaded/stored as one 128-bit word
+
+// ---- device-side view of a Hamiltonian handle -------------------------------
+struct HamView {
+    int n_orb, n_alpha, n_beta;
+    double e_nuc;
+    const float* h1;      // (n,n)  float32 h1[p*n+q]                molecular.py:68
+    const float* g;       // (n,n,n,n) float32 (pq|rs) chemist order  molecular.py:69
+    const float* w;       // w[x,y,z,u] = fp32(g[x,y,z,u] - g[x,u,z,y]) same-spin value (molecular.py:265,287)
+    const double* hdiag;  // h_pp
+    const double* jks;    // 0.5*(J_pq+J_qp) - 0.5*(K_pq+K_qp)   (molecular.py:163-182, p!=q)
+    const double* jab;    // J_pq = g[p,p,q,q]                   (molecular.py:171)
+};
+
+FGK_HD int fgk_popc(u64 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+FGK_HD int fgk_clz(u64 x)   // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return __builtin_clzll(x);
+#endif
+}
+
+// bit of orbital p inside a spin word
+FGK_HD u64 orb_bit(int n_orb, int p) { return 1ull << (n_orb - 1 - p); }
+
+// mask of the orbitals with index < p (they sit in the bits above orbital p's bit)
+FGK_HD u64 below_mask(int n_orb, int p) { return (~0ull << (n_orb - 1 - p)) << 1; }
+
+// k-th (0-based, ascending orbital index) set orbital of word x; x has > k bits set
+FGK_HD int nth_orbital(u64 x, int n_orb, int k)
+{
+    for (int i = 0; i < k; i++) x &= ~(1ull << (63 - fgk_clz(x)));
+    return n_orb - 1 - (63 - fgk_clz(x));
+}
+
+// Jordan-Wigner sign of a+_p a_q inside one spin block (molecular.py:379-389):
+// parity of the occupied orbitals strictly between p and q.  Orbitals of the
+// other spin block never lie between two same-spin sites.
+FGK_HD int sign1_parity(u64 word, int n_orb, int p, int q)
+{
+    int lo = p < q ? p : q, hi = p < q ? q : p;
+    u64 between = below_mask(n_orb, hi) & ~below_mask(n_orb, lo) & ~orb_bit(n_orb, lo);
+    return fgk_popc(word & between) & 1;
+}
+
+// The reference's double-excitation sign (molecular.py:391-423), evaluated on
+// the KET {a,b} for a+_p a+_r a_s a_q given as SITE indices (0..2n-1).
+// total = P(p) + P(r) + P(s) + P(q) + [p<s] + [r<s] + [p<q] + [r<q]
+//         - [q<r] c_q - [q<s] c_q - [s<q] c_s,   P(x) = #occupied sites < x.
+// Returns total mod 2 (1 => sign -1).  No assumption on the order of p,r,q,s.
+FGK_HD int sign2_parity(u64 a, u64 b, int n_orb, int p, int r, int q, int s)
+{
+    u64 ma = 0, mb = 0;
+    int nbeta = 0;
+    const int st[4] = {p, r, s, q};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; i++) {
+        int x = st[i];
+        if (x < n_orb) ma ^= below_mask(n_orb, x);
+        else { mb ^= below_mask(n_orb, x - n_orb); nbeta++; }
+    }
+    int t = fgk_popc(a & ma) + fgk_popc(b & mb) + nbeta * fgk_popc(a);
+    int cq = (q < n_orb) ? (int)((a >> (n_orb - 1 - q)) & 1) : (int)((b >> (2 * n_orb - 1 - q)) & 1);
+    int cs = (s < n_orb) ? (int)((a >> (n_orb - 1 - s)) & 1) : (int)((b >> (2 * n_orb - 1 - s)) & 1);
+    t += (p < s) + (r < s) + (p < q) + (r < q);
+    t -= (q < r) ? cq : 0;
+    t -= (q < s) ? cq : 0;
+    t -= (s < q) ? cs : 0;
+    return t & 1;
+}
+
+// index into an (n,n,n,n) table
+FGK_HD size_t idx4(int n, int x, int y, int z, int u)
+{
+    return (((size_t)x * n + y) * n + z) * n + u;
+}
+
+// decode t in [0, m(m-1)/2) -> (k<l), row-major over k (the i<j / k<l loops of
+// molecular.py:257-264).
+FGK_HD void tri_decode(int m, int t, int& k, int& l)
+{
+    // offset(k) = k*(2m-k-1)/2
+    float fm = (float)(2 * m - 1);
+#if defined(__CUDA_ARCH__)
+    int kk = (int)((fm - sqrtf(fm * fm - 8.0f * (float)t)) * 0.5f);
+#else
+    int kk = (int)((fm - __builtin_sqrtf(fm * fm - 8.0f * (float)t)) * 0.5f);
+#endif
+    if (kk < 0) kk = 0;
+    if (kk > m - 2) kk = m - 2;
+    while (kk > 0 && kk * (2 * m - kk - 1) / 2 > t) kk--;
+    while ((kk + 1) * (2 * m - kk - 2) / 2 <= t) kk++;
+    k = kk;
+    l = t - kk * (2 * m - kk - 1) / 2 + kk + 1;
+}
+
+// 64-bit mix of a determinant (splitmix/murmur finaliser); upper 32 bits are the
+// tag stored next to the index in the basis table, lower bits pick the slot.
+FGK_HD u64 det_hash(u64 a, u64 b)
+{
+    u64 h = a * 0x9E3779B97F4A7C15ull;
+    h ^= (b + 0xD6E8FEB86659FD93ull) * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 29;
+    h *= 0x9FB21C651E98DF25ull;
+    h ^= h >> 32;
+    return h;
+}
+
+FGK_HD u64 word_hash(u64 a)
+{
+    u64 h = (a + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 29;
+    return h;
+}
+
+// ---- one excitation of a determinant D --------------------------------------
+// cls: 0 = alpha single, 1 = beta single, 2 = alpha-alpha, 3 = beta-beta, 4 = alpha-beta
+// (h0,h1) orbitals emptied in D, (e0,e1) orbitals filled (h1/e1 unused for
+// singles; for cls 4, h0/e0 are alpha and h1/e1 beta orbitals).  For same-spin
+// doubles h0<h1 and e0<e1.
+struct Excitation { int cls, h0, h1, e0, e1; };
+
+FGK_HD fgk_det apply_excitation(fgk_det d, int n, const Excitation& x)
+{
+    switch (x.cls) {
+    case 0: d.a ^= orb_bit(n, x.h0) | orb_bit(n, x.e0); break;
+    case 1: d.b ^= orb_bit(n, x.h0) | orb_bit(n, x.e0); break;
+    case 2: d.a ^= orb_bit(n, x.h0) | orb_bit(n, x.h1) | orb_bit(n, x.e0) | orb_bit(n, x.e1); break;
+    case 3: d.b ^= orb_bit(n, x.h0) | orb_bit(n, x.h1) | orb_bit(n, x.e0) | orb_bit(n, x.e1); break;
+    default:
+        d.a ^= orb_bit(n, x.h0) | orb_bit(n, x.e0);
+        d.b ^= orb_bit(n, x.h1) | orb_bit(n, x.e1);
+    }
+    return d;
+}
+
+// KET element: the value the reference's get_connections(ket) attaches to the
+// connection ket -> (ket with x applied), molecular.py:234-318.
+// Returns false if the reference's |val| > 1e-12 filter drops it.
+// `ldf` abstracts the table read (plain load on the host, __ldg on the device).
+template <class Ld>
+FGK_HD bool ket_element(const HamView& H, fgk_det ket, const Excitation& x, Ld ldf, float& out)
+{
+    const int n = H.n_orb;
+    float val;
+    int par;
+    switch (x.cls) {
+    case 0:   // a+_p a_q, p = e0, q = h0 : sign * h_pq          (:234-242)
+    case 1: { //                                                  (:244-251)
+        val = ldf(H.h1 + (size_t)x.e0 * n + x.h0);
+        par = sign1_parity(x.cls == 0 ? ket.a : ket.b, n, x.e0, x.h0);
+        break;
+    }
+    case 2: { // q=h0 < s=h1, p=e0 < r=e1 : g[p,q,r,s]-g[p,s,r,q] (:254-274)
+        val = ldf(H.w + idx4(n, x.e0, x.h0, x.e1, x.h1));
+        par = sign2_parity(ket.a, ket.b, n, x.e0, x.e1, x.h0, x.h1);
+        break;
+    }
+    case 3: { //                                                  (:276-300)
+        val = ldf(H.w + idx4(n, x.e0, x.h0, x.e1, x.h1));
+        par = sign2_parity(ket.a, ket.b, n, x.e0 + n, x.e1 + n, x.h0 + n, x.h1 + n);
+        break;
+    }
+    default: { // q=h0 (alpha), s=h1 (beta), p=e0, r=e1 : g[p,q,r,s] (:302-318)
+        val = ldf(H.g + idx4(n, x.e0, x.h0, x.e1, x.h1));
+        par = sign2_parity(ket.a, ket.b, n, x.e0, x.e1 + n, x.h0, x.h1 + n);
+    }
+    }
+    float av = val < 0.f ? -val : val;
+    if (!(av > 1e-12f)) return false;
+    out = par ? -val : val;
+    return true;
+}
+
+// BRA element: <D|H|j> with j = D + x, i.e. what get_connections(j) reports for
+// the connection j -> D.  Seen from j the holes are x's particles and vice versa.
+template <class Ld>
+FGK_HD bool bra_element(const HamView& H, fgk_det bra, const Excitation& x, Ld ldf, float& out)
+{
+    fgk_det ket = apply_excitation(bra, H.n_orb, x);
+    Excitation rx;
+    rx.cls = x.cls; rx.h0 = x.e0; rx.h1 = x.e1; rx.e0 = x.h0; rx.e1 = x.h1;
+    return ket_element(H, ket, rx, ldf, out);
+}
+
+// FP64 diagonal <D|H|D> on the float32-rounded tables (molecular.py:133-184 in
+// bit form).  `ldd` abstracts the table read.
+template <class Ldd>
+FGK_HD double diag_element(const HamView& H, fgk_det d, Ldd ldd)
+{
+    const int n = H.n_orb;
+    double e = H.e_nuc;
+    u64 xa = d.a;
+    while (xa) {
+        int bp = 63 - fgk_clz(xa);
+        xa &= ~(1ull << bp);
+        int p = n - 1 - bp;
+        e += ldd(H.hdiag + p);
+        u64 ya = xa;                      // orbitals q > p of the same spin
+        while (ya) {
+            int bq = 63 - fgk_clz(ya);
+            ya &= ~(1ull << bq);
+            e += ldd(H.jks + (size_t)p * n + (n - 1 - bq));
+        }
+        u64 yb = d.b;                     // every beta orbital (p == q included, :171)
+        while (yb) {
+            int bq = 63 - fgk_clz(yb);
+            yb &= ~(1ull << bq);
+            e += ldd(H.jab + (size_t)p * n + (n - 1 - bq));
+        }
+    }
+    u64 xb = d.b;
+    while (xb) {
+        int bp = 63 - fgk_clz(xb);
+        xb &= ~(1ull << bp);
+        int p = n - 1 - bp;
+        e += ldd(H.hdiag + p);
+        u64 yb = xb;
+        while (yb) {
+            int bq = 63 - fgk_clz(yb);
+            yb &= ~(1ull << bq);
+            e += ldd(H.jks + (size_t)p * n + (n - 1 - bq));
+        }
+    }
+    return e;
+}
+
+// ---- per-determinant enumeration context -------------------------------------
+// Orbital lists in ascending orbital index (np.where order, molecular.py:220-223).
+// On the device they live in shared memory, one set per warp.
+struct DetCtx {
+    int n;                 // n_orb
+    fgk_det d;
+    const uint8_t *occ_a, *virt_a, *occ_b, *virt_b;
+    int noa, nva, nob, nvb;
+    int n_s;               // singles index space  : n*n   (p = t / n, q = t % n)
+    int n_aa, n_bb, n_ab;  // doubles index spaces : C(noa,2)C(nva,2), C(nob,2)C(nvb,2), noa*nob*nva*nvb
+};
+
+FGK_HD void detctx_sizes(DetCtx& c)
+{
+    c.n_s = c.n * c.n;
+    c.n_aa = (c.noa * (c.noa - 1) / 2) * (c.nva * (c.nva - 1) / 2);
+    c.n_bb = (c.nob * (c.nob - 1) / 2) * (c.nvb * (c.nvb - 1) / 2);
+    c.n_ab = c.noa * c.nob * c.nva * c.nvb;
+}
+
+// host-side list construction (the kernels build the same lists with one lane per orbital)
+inline void detctx_fill_host(DetCtx& c, int n, fgk_det d, uint8_t* buf /* 4*64 bytes */)
+{
+    uint8_t *oa = buf, *va = buf + 64, *ob = buf + 128, *vb = buf + 192;
+    c.n = n; c.d = d; c.noa = c.nva = c.nob = c.nvb = 0;
+    for (int p = 0; p < n; p++) {
+        if (d.a & orb_bit(n, p)) oa[c.noa++] = (uint8_t)p; else va[c.nva++] = (uint8_t)p;
+        if (d.b & orb_bit(n, p)) ob[c.nob++] = (uint8_t)p; else vb[c.nvb++] = (uint8_t)p;
+    }
+    c.occ_a = oa; c.virt_a = va; c.occ_b = ob; c.virt_b = vb;
+    detctx_sizes(c);
+}
+
+// singles index t -> (p = t / n particle, q = t % n hole); valid_a / valid_b say
+// whether the alpha / beta move exists in D (occupancy only; the |h_pq| filter is
+// applied by ket_element/bra_element).  Reference order: p outer, q inner, alpha
+// before beta for each pair (molecular.py:234-251).
+FGK_HD void decode_single(const DetCtx& c, int t, int& p, int& q, bool& valid_a, bool& valid_b)
+{
+    p = t / c.n;
+    q = t - p * c.n;
+    u64 bp = orb_bit(c.n, p), bq = orb_bit(c.n, q);
+    valid_a = (p != q) && (c.d.a & bq) && !(c.d.a & bp);
+    valid_b = (p != q) && (c.d.b & bq) && !(c.d.b & bp);
+}
+
+// doubles: stage 2 = alpha-alpha, 3 = beta-beta, 4 = alpha-beta; t inside the
+// stage's index space, reference loop order (molecular.py:257-264, 279-286, 303-306).
+FGK_HD void decode_double(const DetCtx& c, int stage, int t, Excitation& x)
+{
+    x.cls = stage;
+    if (stage == 4) {
+        int l = t % c.nvb; t /= c.nvb;
+        int k = t % c.nva; t /= c.nva;
+        int j = t % c.nob; t /= c.nob;
+        x.h0 = c.occ_a[t]; x.h1 = c.occ_b[j]; x.e0 = c.virt_a[k]; x.e1 = c.virt_b[l];
+        return;
+    }
+    const uint8_t* occ = stage == 2 ? c.occ_a : c.occ_b;
+    const uint8_t* virt = stage == 2 ? c.virt_a : c.virt_b;
+    int no = stage == 2 ? c.noa : c.nob, nv = stage == 2 ? c.nva : c.nvb;
+    int npp = nv * (nv - 1) / 2;
+    int hp = t / npp, pp = t - hp * npp;
+    int i, j, k, l;
+    tri_decode(no, hp, i, j);
+    tri_decode(nv, pp, k, l);
+    x.h0 = occ[i]; x.h1 = occ[j]; x.e0 = virt[k]; x.e1 = virt[l];
+}

@@ -1,0 +1,120 @@
+// fgk_hostcheck.cpp -- CPU self-check of the kernels' index arithmetic.
+//
+// NOT a fallback and never imported by the product path: it exists so that the
+// "not gpu" test tier can run the exact __host__ __device__ functions the CUDA
+// kernels use (fgk_core.cuh: decode, sign, element, diagonal) against the
+// oracle on a machine without a GPU.  Built by tests with plain g++.
+#include <map>
+#include <utility>
+#include "fgk_core.cuh"
+#include "fgk_tables.h"
+
+struct HcHam { HostTables T; HamView V; };
+
+static inline float ldf_host(const float* p) { return *p; }
+static inline double ldd_host(const double* p) { return *p; }
+
+extern "C" {
+
+void* hc_ham_create(const double* h1, const double* g, int n_orb, int n_alpha, int n_beta, double e_nuc)
+{
+    HcHam* H = new HcHam();
+    build_host_tables(h1, g, n_orb, H->T);
+    H->V.n_orb = n_orb; H->V.n_alpha = n_alpha; H->V.n_beta = n_beta; H->V.e_nuc = e_nuc;
+    H->V.h1 = H->T.h1.data(); H->V.g = H->T.g.data(); H->V.w = H->T.w.data();
+    H->V.hdiag = H->T.hdiag.data(); H->V.jks = H->T.jks.data(); H->V.jab = H->T.jab.data();
+    return H;
+}
+void hc_ham_destroy(void* h) { delete (HcHam*)h; }
+
+void hc_diag(void* h, const u64* dets, long n, double* out)
+{
+    HcHam* H = (HcHam*)h;
+    for (long i = 0; i < n; i++) {
+        fgk_det d = {dets[2 * i], dets[2 * i + 1]};
+        out[i] = diag_element(H->V, d, ldd_host);
+    }
+}
+
+// ket-mode enumeration in reference order; returns count, stores up to cap
+long hc_connections(void* h, u64 a, u64 b, u64* out_dets, float* out_el, long cap)
+{
+    HcHam* H = (HcHam*)h;
+    uint8_t buf[256];
+    DetCtx c;
+    fgk_det d = {a, b};
+    detctx_fill_host(c, H->V.n_orb, d, buf);
+    long m = 0;
+    auto emit = [&](const Excitation& x) {
+        float v;
+        if (!ket_element(H->V, d, x, ldf_host, v)) return;
+        if (m < cap) {
+            fgk_det o = apply_excitation(d, c.n, x);
+            out_dets[2 * m] = o.a; out_dets[2 * m + 1] = o.b; out_el[m] = v;
+        }
+        m++;
+    };
+    for (int t = 0; t < c.n_s; t++) {
+        int p, q; bool va, vb;
+        decode_single(c, t, p, q, va, vb);
+        Excitation x; x.h1 = x.e1 = 0; x.h0 = q; x.e0 = p;
+        if (va) { x.cls = 0; emit(x); }
+        if (vb) { x.cls = 1; emit(x); }
+    }
+    const int sizes[3] = {c.n_aa, c.n_bb, c.n_ab};
+    for (int st = 2; st <= 4; st++)
+        for (int t = 0; t < sizes[st - 2]; t++) {
+            Excitation x;
+            decode_double(c, st, t, x);
+            emit(x);
+        }
+    return m;
+}
+
+// bra-mode row i of the projected H over `basis` (n dets): every (col j, value)
+// with j = basis index of D_i + x.  mode 0 = raw directed <i|H|j>;
+// mode 1 = symmetrised 0.5*(<i|H|j> + <j|H|i>).  Diagonal included first.
+long hc_bra_row(void* h, const u64* basis, long n, long i, int mode, int* out_cols,
+                double* out_vals, long cap)
+{
+    HcHam* H = (HcHam*)h;
+    std::map<std::pair<u64, u64>, long> index;
+    for (long k = 0; k < n; k++) index[{basis[2 * k], basis[2 * k + 1]}] = k;   // last wins
+    uint8_t buf[256];
+    DetCtx c;
+    fgk_det d = {basis[2 * i], basis[2 * i + 1]};
+    detctx_fill_host(c, H->V.n_orb, d, buf);
+    long m = 0;
+    if (m < cap) { out_cols[m] = (int)i; out_vals[m] = diag_element(H->V, d, ldd_host); }
+    m++;
+    auto emit = [&](const Excitation& x) {
+        fgk_det o = apply_excitation(d, c.n, x);
+        auto it = index.find({o.a, o.b});
+        if (it == index.end()) return;
+        float vij = 0.f, vji = 0.f;
+        bool kij = bra_element(H->V, d, x, ldf_host, vij);
+        bool kji = (mode == 1) ? ket_element(H->V, d, x, ldf_host, vji) : false;
+        if (!kij && !kji) return;
+        double v = mode == 1 ? 0.5 * ((double)(kij ? vij : 0.f) + (double)(kji ? vji : 0.f))
+                             : (double)vij;
+        if (m < cap) { out_cols[m] = (int)it->second; out_vals[m] = v; }
+        m++;
+    };
+    for (int t = 0; t < c.n_s; t++) {
+        int p, q; bool va, vb;
+        decode_single(c, t, p, q, va, vb);
+        Excitation x; x.h1 = x.e1 = 0; x.h0 = q; x.e0 = p;
+        if (va) { x.cls = 0; emit(x); }
+        if (vb) { x.cls = 1; emit(x); }
+    }
+    const int sizes[3] = {c.n_aa, c.n_bb, c.n_ab};
+    for (int st = 2; st <= 4; st++)
+        for (int t = 0; t < sizes[st - 2]; t++) {
+            Excitation x;
+            decode_double(c, st, t, x);
+            emit(x);
+        }
+    return m;
+}
+
+}  // extern "C"

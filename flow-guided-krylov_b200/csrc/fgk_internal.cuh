@@ -1,0 +1,183 @@
+// fgk_internal.cuh -- handles, error plumbing and warp-level helpers shared by
+// the .cu translation units of libfgk_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/fgk_b200.h"
+#include "fgk_core.cuh"
+
+typedef long long i64;
+
+// ---- error plumbing -----------------------------------------------------------
+std::string& fgk_err_slot();
+int fgk_fail(int code, const char* fmt, ...);
+
+#define FGK_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return fgk_fail(FGK_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,  \
+                            cudaGetErrorString(e__));                                   \
+    } while (0)
+
+#define FGK_LAUNCH_CHECK()                                                              \
+    do {                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess)                                                         \
+            return fgk_fail(FGK_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__,        \
+                            __LINE__, cudaGetErrorString(e__));                         \
+    } while (0)
+
+// ---- handles --------------------------------------------------------------------
+struct fgk_ham {
+    int device;
+    HamView v;          // device pointers
+    float *h1, *g, *w;
+    double *hdiag, *jks, *jab;
+};
+
+struct IndexView {
+    const fgk_det* dets;
+    i64 n;
+    const u64* table;   // (tag << 32 | index), empty = ~0
+    u64 mask;
+    const u64* aset;    // distinct alpha strings, empty = ~0
+    u64 amask;
+    const u64* bset;
+    u64 bmask;
+};
+
+struct fgk_index {
+    int device;
+    IndexView v;
+    u64 *table, *aset, *bset;
+    i64 n_alpha_strings, n_beta_strings;
+};
+
+struct Pt2View {
+    u64* table;         // (tag << 32 | slot), empty = ~0
+    u64 mask;
+    fgk_det* keys;      // pool
+    double* sums;
+    i64 capacity;
+    unsigned long long* counters;   // [0] slots used, [1] raw candidates tested, [2] overflow
+};
+
+struct fgk_pt2 {
+    int device;
+    Pt2View v;
+};
+
+static const u64 FGK_EMPTY = ~0ull;
+static const int FGK_WARPS_PER_BLOCK = 8;
+static const int FGK_BLOCK = FGK_WARPS_PER_BLOCK * 32;
+
+int fgk_sm_count(int device);
+
+// ---- device helpers ---------------------------------------------------------------
+#if defined(__CUDACC__)
+
+struct LdgF { __device__ __forceinline__ float operator()(const float* p) const { return __ldg(p); } };
+struct LdgD { __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); } };
+
+struct WarpLists { uint8_t occ_a[64], virt_a[64], occ_b[64], virt_b[64]; };
+
+// one lane per orbital builds the ascending occupied / virtual lists of d
+__device__ __forceinline__ void warp_build_ctx(DetCtx& c, int n, fgk_det d, WarpLists& L, int lane)
+{
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) {
+        u64 bit = orb_bit(n, p), below = below_mask(n, p);
+        int ka = __popcll(d.a & below), kb = __popcll(d.b & below);
+        if (d.a & bit) L.occ_a[ka] = (uint8_t)p; else L.virt_a[p - ka] = (uint8_t)p;
+        if (d.b & bit) L.occ_b[kb] = (uint8_t)p; else L.virt_b[p - kb] = (uint8_t)p;
+    }
+    __syncwarp();
+    c.n = n; c.d = d;
+    c.noa = __popcll(d.a); c.nva = n - c.noa;
+    c.nob = __popcll(d.b); c.nvb = n - c.nob;
+    c.occ_a = L.occ_a; c.virt_a = L.virt_a; c.occ_b = L.occ_b; c.virt_b = L.virt_b;
+    detctx_sizes(c);
+}
+
+// Walk every excitation of c.d in the reference's order, 32 index slots per step.
+// fs(valid_a, valid_b, p, q)  -- singles step (alpha then beta for the pair)
+// fd(valid, x)                -- doubles step
+// Both are called by ALL lanes, convergently, so they may use warp collectives.
+template <class FS, class FD>
+__device__ __forceinline__ void warp_enumerate(const DetCtx& c, int lane, FS&& fs, FD&& fd)
+{
+    for (int t0 = 0; t0 < c.n_s; t0 += 32) {
+        int t = t0 + lane, p = 0, q = 0;
+        bool va = false, vb = false;
+        if (t < c.n_s) decode_single(c, t, p, q, va, vb);
+        fs(va, vb, p, q);
+    }
+#pragma unroll 1
+    for (int st = 2; st <= 4; st++) {
+        const int size = st == 2 ? c.n_aa : (st == 3 ? c.n_bb : c.n_ab);
+        for (int t0 = 0; t0 < size; t0 += 32) {
+            int t = t0 + lane;
+            Excitation x;
+            x.cls = st; x.h0 = x.h1 = x.e0 = x.e1 = 0;
+            bool valid = t < size;
+            if (valid) decode_double(c, st, t, x);
+            fd(valid, x);
+        }
+    }
+}
+
+__device__ __forceinline__ bool set_has(const u64* set, u64 mask, u64 w)
+{
+    u64 slot = word_hash(w) & mask;
+    while (true) {
+        u64 e = __ldg(set + slot);
+        if (e == w) return true;
+        if (e == FGK_EMPTY) return false;
+        slot = (slot + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ int index_find(const IndexView& I, fgk_det o)
+{
+    u64 h = det_hash(o.a, o.b);
+    u64 tag = h >> 32, slot = h & I.mask;
+    while (true) {
+        u64 e = __ldg(I.table + slot);
+        if (e == FGK_EMPTY) return -1;
+        if ((e >> 32) == tag) {
+            unsigned idx = (unsigned)(e & 0xffffffffu);
+            ulonglong2 k = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + idx);
+            if (k.x == o.a && k.y == o.b) return (int)idx;
+        }
+        slot = (slot + 1) & I.mask;
+    }
+}
+
+// cheap necessary conditions first (alpha / beta string sets are small and
+// L1-resident), then the full-key probe.  cls tells which words changed.
+__device__ __forceinline__ int index_find_filtered(const IndexView& I, fgk_det o, int cls)
+{
+    if (cls != 1 && cls != 3) { if (!set_has(I.aset, I.amask, o.a)) return -1; }
+    if (cls != 0 && cls != 2) { if (!set_has(I.bset, I.bmask, o.b)) return -1; }
+    return index_find(I, o);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ i64 warp_sum_i64(i64 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,264 @@
+// fgk_pt2.cu -- K7/K8: PT2 residual expansion.
+//
+// One warp per SOURCE determinant j ("ket mode", exactly the connections the
+// reference's get_connections(j) emits): every connection x that is not in the
+// basis adds c_j * <x|H|j> to the FP64 accumulator of x in a device hash map
+// (open addressing; 64-bit table entries tag<<32|slot pointing into a pool of
+// 16-byte keys + 8-byte sums).  This is phase 1 of
+// SelectedCIExpander._find_important_configs (residual_expansion.py:498-522) --
+// there a Python dict keyed by hash(bytes).  fgk_pt2_export is phase 2
+// (:527-548): diagonal of every candidate and coupling^2 / (|E - E_x| + 1e-10).
+#include "fgk_internal.cuh"
+
+static u64 pow2_at_least(u64 x)
+{
+    u64 p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+__device__ __forceinline__ void atomic_max_abs(double* addr, double v)
+{
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(addr),
+              (unsigned long long)__double_as_longlong(fabs(v)));
+}
+
+// insert-or-accumulate; returns false on pool overflow
+__device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, double val, int mode)
+{
+    u64 h = det_hash(o.a, o.b);
+    u64 tag = h >> 32, slot = h & W.mask;
+    long long mine = -1;        // pool slot this thread allocated (at most one)
+    bool ok = true;
+    while (true) {
+        u64 e = *reinterpret_cast<volatile u64*>(W.table + slot);
+        if (e == FGK_EMPTY) {
+            if (mine < 0) {
+                mine = (long long)atomicAdd(W.counters, 1ull);
+                if (mine >= W.capacity) { atomicExch(W.counters + 2, 1ull); ok = false; break; }
+                reinterpret_cast<ulonglong2*>(W.keys)[mine] = make_ulonglong2(o.a, o.b);
+                __threadfence();
+            }
+            u64 prev = atomicCAS((unsigned long long*)(W.table + slot), FGK_EMPTY,
+                                 (tag << 32) | (u64)(unsigned)mine);
+            if (prev == FGK_EMPTY) {
+                if (mode == FGK_PT2_MAXABS) atomic_max_abs(W.sums + mine, val);
+                else atomicAdd(W.sums + mine, val);
+                mine = -1;
+                break;
+            }
+            e = prev;               // somebody else took the slot: inspect it
+        }
+        if ((e >> 32) == tag) {
+            unsigned ps = (unsigned)(e & 0xffffffffu);
+            // L2 read: the key was published with __threadfence before the CAS
+            ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(W.keys) + ps);
+            if (k.x == o.a && k.y == o.b) {
+                if (mode == FGK_PT2_MAXABS) atomic_max_abs(W.sums + ps, val);
+                else atomicAdd(W.sums + ps, val);
+                break;
+            }
+        }
+        slot = (slot + 1) & W.mask;
+    }
+    if (mine >= 0 && mine < W.capacity)   // allocated but lost the race: mark the slot dead
+        reinterpret_cast<ulonglong2*>(W.keys)[mine] = make_ulonglong2(FGK_EMPTY, FGK_EMPTY);
+    return ok;
+}
+
+__global__ void __launch_bounds__(FGK_BLOCK)
+k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_idx,
+                 const double* __restrict__ coeff, i64 n_src, int mode, unsigned n_pass,
+                 unsigned pass_id)
+{
+    __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
+    const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
+    LdgF ldf;
+    i64 tested = 0;
+    for (i64 sidx = warp0; sidx < n_src; sidx += nwarps) {
+        const i64 j = __ldg(src_idx + sidx);
+        const double cj = __ldg(coeff + sidx);
+        ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + j);
+        fgk_det d = {dv.x, dv.y};
+        DetCtx c;
+        warp_build_ctx(c, H.n_orb, d, s_lists[wib], lane);
+        auto visit = [&](bool valid, const Excitation& x) {
+            if (!valid) return;
+            float el;
+            if (!ket_element(H, d, x, ldf, el)) return;          // reference filter
+            fgk_det o = apply_excitation(d, c.n, x);
+            if (n_pass > 1 && (unsigned)((det_hash(o.a, o.b) >> 40) % n_pass) != pass_id) return;
+            tested++;
+            if (index_find_filtered(I, o, x.cls) >= 0) return;   // in the basis (:513)
+            pt2_upsert(W, o, cj * (double)el, mode);
+        };
+        warp_enumerate(
+            c, lane,
+            [&](bool va, bool vb, int p, int q) {
+                Excitation x;
+                x.h0 = q; x.e0 = p; x.h1 = 0; x.e1 = 0;
+                x.cls = 0;
+                visit(va, x);
+                x.cls = 1;
+                visit(vb, x);
+            },
+            visit);
+    }
+    tested = warp_sum_i64(tested);
+    if (lane == 0 && tested) atomicAdd(W.counters + 1, (unsigned long long)tested);
+}
+
+__global__ void __launch_bounds__(256)
+k_pt2_merge(Pt2View W, const fgk_det* __restrict__ dets, const double* __restrict__ vals, i64 m, int mode)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + i);
+        fgk_det o = {d.x, d.y};
+        pt2_upsert(W, o, __ldg(vals + i), mode);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_pt2_export(HamView H, bool have_h, Pt2View W, i64 n_slots, double energy,
+             fgk_det* __restrict__ out_dets, double* __restrict__ out_coupling,
+             double* __restrict__ out_diag, double* __restrict__ out_importance,
+             uint8_t* __restrict__ out_valid)
+{
+    LdgD ldd;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_slots; k += (i64)gridDim.x * blockDim.x) {
+        ulonglong2 d = reinterpret_cast<const ulonglong2*>(W.keys)[k];
+        bool dead = (d.x == FGK_EMPTY && d.y == FGK_EMPTY);
+        double cpl = W.sums[k];
+        if (out_dets) reinterpret_cast<ulonglong2*>(out_dets)[k] = d;
+        if (out_coupling) out_coupling[k] = dead ? 0.0 : cpl;
+        if (out_valid) out_valid[k] = dead ? 0 : 1;
+        if (have_h) {
+            double ex = 0.0, imp = -1.0;
+            if (!dead) {
+                fgk_det dd = {d.x, d.y};
+                ex = diag_element(H, dd, ldd);
+                imp = cpl * cpl / (fabs(energy - ex) + 1e-10);   // residual_expansion.py:547-548
+            }
+            if (out_diag) out_diag[k] = ex;
+            if (out_importance) out_importance[k] = imp;
+        }
+    }
+}
+
+extern "C" int fgk_pt2_create(int64_t capacity, int device, fgk_pt2_t* out)
+{
+    if (!out || capacity < 1) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: bad argument");
+    if (capacity >= (1ll << 32) - 1) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_pt2_create: capacity >= 2^32");
+    FGK_CUDA(cudaSetDevice(device));
+    fgk_pt2* P = new fgk_pt2();
+    P->device = device;
+    u64 tsize = pow2_at_least((u64)capacity * 2 < 1024 ? 1024 : (u64)capacity * 2);
+    P->v.capacity = capacity;
+    P->v.mask = tsize - 1;
+    P->v.table = nullptr; P->v.keys = nullptr; P->v.sums = nullptr; P->v.counters = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&P->v.table, tsize * sizeof(u64))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&P->v.keys, (size_t)capacity * sizeof(fgk_det))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&P->v.sums, (size_t)capacity * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&P->v.counters, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+        cudaFree(P->v.table); cudaFree(P->v.keys); cudaFree(P->v.sums); cudaFree(P->v.counters);
+        delete P;
+        return fgk_fail(FGK_ERR_CUDA, "fgk_pt2_create: cudaMalloc -> %s", cudaGetErrorString(e));
+    }
+    *out = P;
+    return fgk_pt2_reset(P, nullptr);
+}
+
+extern "C" int fgk_pt2_destroy(fgk_pt2_t ws)
+{
+    if (!ws) return FGK_OK;
+    cudaSetDevice(ws->device);
+    cudaFree(ws->v.table); cudaFree(ws->v.keys); cudaFree(ws->v.sums); cudaFree(ws->v.counters);
+    delete ws;
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_reset(fgk_pt2_t ws, void* stream)
+{
+    if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_reset: null handle");
+    FGK_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FGK_CUDA(cudaMemsetAsync(ws->v.table, 0xFF, (ws->v.mask + 1) * sizeof(u64), st));
+    FGK_CUDA(cudaMemsetAsync(ws->v.sums, 0, (size_t)ws->v.capacity * sizeof(double), st));
+    FGK_CUDA(cudaMemsetAsync(ws->v.counters, 0, 4 * sizeof(unsigned long long), st));
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, const int64_t* src_idx,
+                                  const double* coeff, int64_t n_src, int mode, int n_pass,
+                                  int pass_id, void* stream)
+{
+    if (!h || !idx || !ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: null handle");
+    if (n_src == 0) return FGK_OK;
+    if (!src_idx || !coeff || n_src < 0 || n_pass < 1 || pass_id < 0 || pass_id >= n_pass)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: bad argument");
+    if (h->device != idx->device || h->device != ws->device)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: device mismatch");
+    FGK_CUDA(cudaSetDevice(h->device));
+    i64 need = (n_src + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
+    i64 cap = (i64)fgk_sm_count(h->device) * 8;
+    int grid = (int)(need < cap ? need : cap);
+    k_pt2_accumulate<<<grid, FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+        h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, mode, (unsigned)n_pass,
+        (unsigned)pass_id);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_merge(fgk_pt2_t ws, const uint64_t* dets, const double* vals, int64_t m,
+                             int mode, void* stream)
+{
+    if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_merge: null handle");
+    if (m == 0) return FGK_OK;
+    if (!dets || !vals || m < 0) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_merge: bad argument");
+    FGK_CUDA(cudaSetDevice(ws->device));
+    i64 need = (m + 255) / 256, cap = (i64)fgk_sm_count(ws->device) * 8;
+    k_pt2_merge<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        ws->v, (const fgk_det*)dets, vals, m, mode);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_count(fgk_pt2_t ws, void* stream, int64_t* n_slots, int64_t* n_raw,
+                             int* overflow)
+{
+    if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_count: null handle");
+    FGK_CUDA(cudaSetDevice(ws->device));
+    unsigned long long hc[4];
+    FGK_CUDA(cudaMemcpyAsync(hc, ws->v.counters, sizeof(hc), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FGK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    i64 used = (i64)hc[0] < ws->v.capacity ? (i64)hc[0] : ws->v.capacity;
+    if (n_slots) *n_slots = used;
+    if (n_raw) *n_raw = (i64)hc[1];
+    if (overflow) *overflow = hc[2] ? 1 : 0;
+    if (hc[2])
+        return fgk_fail(FGK_ERR_CAPACITY, "fgk_pt2: candidate pool overflow (capacity %lld)",
+                        (long long)ws->v.capacity);
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy,
+                              uint64_t* out_dets, double* out_coupling, double* out_diag,
+                              double* out_importance, uint8_t* out_valid, void* stream)
+{
+    if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_export: null handle");
+    if (n_slots == 0) return FGK_OK;
+    if (n_slots < 0 || n_slots > ws->v.capacity) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_export: bad n_slots");
+    FGK_CUDA(cudaSetDevice(ws->device));
+    HamView hv;
+    if (h) hv = h->v; else { hv = HamView(); }
+    i64 need = (n_slots + 255) / 256, cap = (i64)fgk_sm_count(ws->device) * 8;
+    k_pt2_export<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        hv, h != nullptr, ws->v, n_slots, energy, (fgk_det*)out_dets, out_coupling, out_diag,
+        out_importance, out_valid);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}

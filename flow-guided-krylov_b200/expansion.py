@@ -1,0 +1,318 @@
+"""Stage-3 residual / PT2 basis expansion over the sm_100a engine.
+
+Host-side mirror of reference src/krylov/residual_expansion.py:
+  ResidualExpansionConfig (:27-57), SelectedCIExpander (:305-554),
+  ResidualBasedExpander (:60-257) -- same constructor and method signatures, same
+  stats dictionaries.  The Python loops over get_connections + dict lookups are
+  replaced by fgk_pt2_* (enumerate -> filter -> hash-accumulate -> diagonal ->
+  importance) and the dense n x n diagonalisation by the device CSR + solvers.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .hamiltonian import BasisIndex, sort_unique_dets
+from .solvers import lowest_eigenpairs
+
+
+@dataclass
+class ResidualExpansionConfig:
+    """residual_expansion.py:27-57 (field for field)."""
+    max_configs_per_iter: int = 100
+    residual_threshold: float = 1e-4
+    max_iterations: int = 10
+    energy_convergence: float = 1e-6
+    min_energy_improvement_mha: float = 0.05
+    stagnation_patience: int = 2
+    max_basis_size: int = 4096
+    use_importance_sampling: bool = True
+    n_importance_samples: int = 10000
+
+
+class Pt2Workspace:
+    """Device hash map candidate -> FP64 accumulator (fgk_pt2_*)."""
+
+    def __init__(self, capacity, device):
+        self.capacity = int(capacity)
+        self.device = device
+        h = C.c_void_p()
+        nat.check(nat.lib().fgk_pt2_create(self.capacity, nat.device_index(device), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                nat.lib().fgk_pt2_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def reset(self):
+        nat.check(nat.lib().fgk_pt2_reset(self._h, nat.stream_ptr(self.device)))
+
+    def accumulate(self, ham, index, src_idx, coeff, mode=nat.PT2_SUM, n_pass=1, pass_id=0):
+        src_idx = src_idx.to(torch.int64).contiguous()
+        coeff = coeff.to(torch.float64).contiguous()
+        nat.check(nat.lib().fgk_pt2_accumulate(
+            ham._h, index._h, self._h, nat.ptr(src_idx, torch.int64), nat.ptr(coeff, torch.float64),
+            src_idx.shape[0], mode, n_pass, pass_id, nat.stream_ptr(self.device)))
+
+    def merge(self, dets, vals, mode=nat.PT2_SUM):
+        dets = dets.contiguous()
+        vals = vals.to(torch.float64).contiguous()
+        nat.check(nat.lib().fgk_pt2_merge(self._h, nat.ptr(dets, torch.int64),
+                                          nat.ptr(vals, torch.float64), dets.shape[0], mode,
+                                          nat.stream_ptr(self.device)))
+
+    def count(self):
+        """-> (slots used, raw candidates tested, overflowed)  [synchronises]"""
+        ns, nr, ov = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        rc = nat.lib().fgk_pt2_count(self._h, nat.stream_ptr(self.device), C.byref(ns), C.byref(nr),
+                                     C.byref(ov))
+        if rc not in (nat.OK, nat.ERR_CAPACITY):
+            nat.check(rc)
+        return ns.value, nr.value, bool(ov.value)
+
+    def export(self, ham, n_slots, energy=0.0):
+        """-> (dets, coupling, diag, importance) of the live candidates."""
+        dev = self.device
+        dets = torch.empty(n_slots, 2, dtype=torch.int64, device=dev)
+        cpl = torch.empty(n_slots, dtype=torch.float64, device=dev)
+        dg = torch.empty(n_slots, dtype=torch.float64, device=dev)
+        imp = torch.empty(n_slots, dtype=torch.float64, device=dev)
+        valid = torch.empty(n_slots, dtype=torch.uint8, device=dev)
+        nat.check(nat.lib().fgk_pt2_export(
+            ham._h if ham is not None else None, self._h, n_slots, float(energy),
+            nat.ptr(dets, torch.int64), nat.ptr(cpl, torch.float64), nat.ptr(dg, torch.float64),
+            nat.ptr(imp, torch.float64), nat.ptr(valid, torch.uint8), nat.stream_ptr(dev)))
+        m = valid.bool()
+        return dets[m], cpl[m], dg[m], imp[m]
+
+
+def _key_sort_order(dets, n_orb):
+    """argsort of packed determinants by ascending unsigned (alpha, beta)."""
+    a, b = dets[:, 0], dets[:, 1]
+    if n_orb == 64:
+        flip = torch.tensor(-2 ** 63, dtype=torch.int64, device=dets.device)
+        a, b = a ^ flip, b ^ flip
+    o = torch.argsort(b, stable=True)
+    return o[torch.argsort(a[o], stable=True)]
+
+
+def select_top_k(dets, score, k, n_orb):
+    """Deterministic top-k: score descending, ties by ascending key (the reference's
+    torch.topk leaves ties unspecified, residual_expansion.py:552)."""
+    n = dets.shape[0]
+    k = min(int(k), n)
+    if k == 0:
+        return dets[:0], score[:0]
+    kth = torch.topk(score, k).values[-1]
+    sure = torch.nonzero(score > kth).squeeze(1)
+    tie = torch.nonzero(score == kth).squeeze(1)
+    need = k - sure.numel()
+    if tie.numel() > need:
+        tie = tie[_key_sort_order(dets[tie], n_orb)[:need]]
+    pick = torch.cat([sure, tie])
+    # final order: score desc, key asc
+    ko = _key_sort_order(dets[pick], n_orb)
+    pick = pick[ko]
+    pick = pick[torch.argsort(score[pick], descending=True, stable=True)]
+    return dets[pick], score[pick]
+
+
+def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
+                   coeff_cut=1e-8, max_passes=64, src_range=None):
+    """Phase 1+2 of _find_important_configs (residual_expansion.py:481-548) for the
+    sources of `index` (optionally only positions src_range=(lo,hi)).
+    Returns (cand_dets, coupling, diag, importance, stats)."""
+    dev = ham.device
+    n = len(index)
+    c32 = coeffs.to(dev).to(torch.float32)                         # :481
+    src = torch.nonzero(c32.abs() > coeff_cut).squeeze(1)          # :489-490
+    if src_range is not None:
+        src = src[(src >= src_range[0]) & (src < src_range[1])]
+    cj = c32[src].double()
+    stats = dict(n_sources=int(src.numel()), raw_candidates=0, passes=1)
+    empty = (torch.empty(0, 2, dtype=torch.int64, device=dev),) + tuple(
+        torch.empty(0, dtype=torch.float64, device=dev) for _ in range(3))
+    if src.numel() == 0:
+        return empty + (stats,)
+    ws = workspace
+    if ws is None:
+        n_conn = _raw_connections_per_det(ham)
+        free = nat.device_info(dev)["free_bytes"]
+        cap = int(min(max(4096, 1.25 * src.numel() * n_conn), 0.5 * free / 40, 2 ** 31))
+        ws = Pt2Workspace(cap, dev)
+    n_pass = 1
+    while True:
+        outs, raw, ok = [], 0, True
+        for p in range(n_pass):
+            ws.reset()
+            ws.accumulate(ham, index, src, cj, mode, n_pass, p)
+            ns, nr, ov = ws.count()
+            if ov:
+                ok = False
+                break
+            raw += nr
+            outs.append(ws.export(ham, ns, energy))
+        if ok:
+            break
+        n_pass *= 2
+        if n_pass > max_passes:
+            raise RuntimeError("PT2 candidate set does not fit the workspace even in "
+                               f"{max_passes} passes (capacity {ws.capacity})")
+    stats.update(raw_candidates=raw, passes=n_pass)
+    if len(outs) == 1:
+        return outs[0] + (stats,)
+    return tuple(torch.cat([o[i] for o in outs]) for i in range(4)) + (stats,)
+
+
+def _raw_connections_per_det(ham):
+    n, na, nb = ham.n_orbitals, ham.n_alpha, ham.n_beta
+    va, vb = n - na, n - nb
+    c2 = lambda m: m * (m - 1) // 2
+    return na * va + nb * vb + c2(na) * c2(va) + c2(nb) * c2(vb) + na * nb * va * vb
+
+
+class SelectedCIExpander:
+    """residual_expansion.py:305-554, same signatures."""
+
+    def __init__(self, hamiltonian, config: ResidualExpansionConfig = None):
+        self.hamiltonian = hamiltonian
+        self.config = config or ResidualExpansionConfig()
+        self.device = getattr(hamiltonian, "device", "cpu")
+        self.last_stats = {}
+
+    # :408-443 -- float64, symmetrised; dense eigh for small n, Davidson above
+    def _diagonalize_packed(self, dets):
+        H = self.hamiltonian
+        P = H.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)
+        w, v = lowest_eigenpairs(P, k=1)
+        return float(w[0]), v[:, 0], P._index
+
+    def _diagonalize(self, basis: torch.Tensor) -> Tuple[float, np.ndarray]:
+        E, v, _ = self._diagonalize_packed(self.hamiltonian.pack(basis))
+        return E, v.cpu().numpy()
+
+    # :451-554
+    def _find_important_packed(self, dets, index, energy, v):
+        H = self.hamiltonian
+        cand, cpl, dg, imp, st = pt2_candidates(H, index, v, energy)
+        self.last_stats = st
+        if cand.shape[0] == 0:
+            return cand, imp
+        return select_top_k(cand, imp, self.config.max_configs_per_iter, H.n_orbitals)
+
+    def _find_important_configs(self, basis, energy, eigenvector):
+        H = self.hamiltonian
+        dets = H.pack(basis)
+        v = torch.as_tensor(np.asarray(eigenvector), dtype=torch.float64, device=self.device)
+        sel, imp = self._find_important_packed(dets, BasisIndex(dets), energy, v)
+        if sel.shape[0] == 0:
+            return (torch.empty(0, basis.shape[1], device=self.device),
+                    torch.empty(0, device=self.device))
+        return H.unpack(sel, basis.dtype), imp.to(H.output_dtype)
+
+    # :334-406
+    def expand_basis(self, current_basis: torch.Tensor) -> Tuple[torch.Tensor, Dict]:
+        H = self.hamiltonian
+        current_basis = current_basis.to(self.device)
+        dets = H.pack(current_basis)
+        energy, v, index = self._diagonalize_packed(dets)
+        sel, _ = self._find_important_packed(dets, index, energy, v)
+        if sel.shape[0] == 0:                                                   # :363-364
+            return current_basis, {'configs_added': 0, 'energy': energy, 'initial_energy': energy,
+                                   'final_energy': energy}
+        expanded = sort_unique_dets(torch.cat([dets, sel], dim=0), H.n_orbitals)   # :367-368
+        new_energy, _, _ = self._diagonalize_packed(expanded)                    # :371
+        energy_improvement = energy - new_energy
+        if energy_improvement < -1e-8:                                           # :378-393
+            return current_basis, {
+                'initial_size': len(current_basis), 'final_size': len(current_basis),
+                'configs_added': 0, 'initial_energy': energy, 'final_energy': energy,
+                'energy_improvement': 0.0, 'energy_improvement_mha': 0.0,
+                'variational_violation': True, 'rejected_energy': new_energy,
+                'rejected_increase_mha': -energy_improvement * 1000}
+        stats = {                                                                # :395-404
+            'initial_size': len(current_basis), 'final_size': int(expanded.shape[0]),
+            'configs_added': int(sel.shape[0]), 'initial_energy': energy,
+            'final_energy': new_energy, 'energy_improvement': energy_improvement,
+            'energy_improvement_mha': energy_improvement * 1000, 'variational_violation': False}
+        return H.unpack(expanded, current_basis.dtype), stats
+
+
+class ResidualBasedExpander:
+    """residual_expansion.py:60-257, same signatures (max |c_j <x|H|j>| instead of PT2)."""
+
+    def __init__(self, hamiltonian, config: ResidualExpansionConfig = None):
+        self.hamiltonian = hamiltonian
+        self.config = config or ResidualExpansionConfig()
+        self.device = getattr(hamiltonian, "device", "cpu")
+
+    # :162-172 -- np.linalg.eigh on the RAW (unsymmetrised) matrix reads the lower triangle
+    def _diagonalize_packed(self, dets):
+        H = self.hamiltonian
+        P = H.projected_csr(dets, nat.H_RAW, packed=True, sort_rows=False)
+        D = P.to_dense()
+        L = torch.tril(D)
+        S = L + torch.tril(D, -1).T
+        w, v = torch.linalg.eigh(S)
+        return float(w[0]), v[:, 0], P._index
+
+    def _diagonalize(self, basis):
+        E, v, _ = self._diagonalize_packed(self.hamiltonian.pack(basis))
+        return E, v.cpu().numpy()
+
+    # :174-253
+    def _find_residual_packed(self, dets, index, v):
+        H = self.hamiltonian
+        cfg = self.config
+        cand, res, _, _, _ = pt2_candidates(H, index, v, 0.0, mode=nat.PT2_MAXABS, coeff_cut=1e-10)
+        if cand.shape[0] == 0:
+            return cand, res
+        res = res.float().double()            # the reference stores residuals in float32 (:228)
+        m = res > cfg.residual_threshold      # :239
+        cand, res = cand[m], res[m]
+        return select_top_k(cand, res, cfg.max_configs_per_iter, H.n_orbitals)
+
+    def expand_basis(self, current_basis, energy: Optional[float] = None,
+                     eigenvector: Optional[np.ndarray] = None):
+        H = self.hamiltonian
+        cfg = self.config
+        current_basis = current_basis.to(self.device)
+        n_current = len(current_basis)
+        dets = H.pack(current_basis)
+        if energy is None or eigenvector is None:
+            energy, v, index = self._diagonalize_packed(dets)
+        else:
+            v = torch.as_tensor(np.asarray(eigenvector), dtype=torch.float64, device=self.device)
+            index = BasisIndex(dets)
+        history = {'energies': [energy], 'basis_sizes': [n_current], 'configs_added': []}
+        cur_e, cur_v = energy, v
+        energy_change = None
+        iteration = -1
+        for iteration in range(cfg.max_iterations):                             # :117-148
+            if dets.shape[0] >= cfg.max_basis_size:
+                break
+            sel, _ = self._find_residual_packed(dets, index, cur_v)
+            if sel.shape[0] == 0:
+                break
+            dets = sort_unique_dets(torch.cat([dets, sel], dim=0), H.n_orbitals)
+            new_e, new_v, index = self._diagonalize_packed(dets)
+            history['energies'].append(new_e)
+            history['basis_sizes'].append(int(dets.shape[0]))
+            history['configs_added'].append(int(sel.shape[0]))
+            energy_change = abs(new_e - cur_e)
+            if energy_change < cfg.energy_convergence:
+                break
+            cur_e, cur_v = new_e, new_v
+        stats = {
+            'initial_basis_size': n_current, 'final_basis_size': int(dets.shape[0]),
+            'configs_added_total': int(dets.shape[0]) - n_current, 'iterations': iteration + 1,
+            'converged': (energy_change < cfg.energy_convergence) if energy_change is not None else True,
+            'final_energy': cur_e, 'history': history}
+        return H.unpack(dets, current_basis.dtype), stats

@@ -1,0 +1,412 @@
+"""MolecularHamiltonian -- host-side mirror of the reference operator interface
+(reference src/hamiltonians/molecular.py:35-942, src/hamiltonians/base.py:9-58)
+over the sm_100a engine.  Same constructor, attribute and method names, same
+argument meaning and the same empty-result conventions; every method body is a
+thin call into libfgk_b200.so.  No CPU path exists.
+
+Parity tiers: connected sets, emission order, off-diagonal values
+and nonzero patterns are bit-exact with the reference; diagonals / energies are
+FP64 on the reference's float32-rounded integrals (the reference's own float32
+einsum has no defined summation order), within 1e-9 Ha of the FP64 oracle.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from itertools import combinations
+from math import comb
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+@dataclass
+class MolecularIntegrals:
+    """Same fields and order as the reference container (molecular.py:22-32)."""
+    h1e: np.ndarray
+    h2e: np.ndarray
+    nuclear_repulsion: float
+    n_electrons: int
+    n_orbitals: int
+    n_alpha: int
+    n_beta: int
+
+
+class ProjectedH:
+    """Rows [row_begin, row_end) of a projected Hamiltonian in device CSR
+    (int64 row_ptr, int32 GLOBAL column ids, FP64 values)."""
+
+    def __init__(self, n, row_ptr, cols, vals, device, row_begin=0, row_end=None, mode=nat.H_RAW,
+                 sorted_rows=False):
+        self.n = int(n)
+        self.row_ptr, self.cols, self.vals = row_ptr, cols, vals
+        self.device = device
+        self.row_begin = int(row_begin)
+        self.row_end = int(n if row_end is None else row_end)
+        self.mode = mode
+        self.sorted_rows = sorted_rows
+
+    @property
+    def n_rows(self):
+        return self.row_end - self.row_begin
+
+    @property
+    def nnz(self):
+        return int(self.vals.numel())
+
+    def sort_rows(self):
+        if not self.sorted_rows and self.nnz:
+            nat.check(nat.lib().fgk_csr_sort_rows(
+                self.n_rows, nat.ptr(self.row_ptr, torch.int64), nat.ptr(self.cols, torch.int32),
+                nat.ptr(self.vals, torch.float64), nat.device_index(self.device),
+                nat.stream_ptr(self.device)))
+        self.sorted_rows = True
+        return self
+
+    def matvec(self, x, out=None):
+        """y = H[row_begin:row_end, :] @ x ; x real FP64 or complex128, length n."""
+        if x.shape[0] != self.n:
+            raise ValueError(f"matvec: x has {x.shape[0]} entries, H has {self.n} columns")
+        dev = nat.device_index(self.device)
+        if x.is_complex():
+            if x.dtype != torch.complex128:
+                x = x.to(torch.complex128)
+            x = x.contiguous()
+            y = out if out is not None else torch.empty(self.n_rows, dtype=torch.complex128, device=x.device)
+            nat.check(nat.lib().fgk_spmv_z(
+                self.n_rows, nat.ptr(self.row_ptr, torch.int64), nat.ptr(self.cols, torch.int32),
+                nat.ptr(self.vals, torch.float64), C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()),
+                dev, nat.stream_ptr(self.device)))
+            return y
+        if x.dtype != torch.float64:
+            x = x.to(torch.float64)
+        x = x.contiguous()
+        y = out if out is not None else torch.empty(self.n_rows, dtype=torch.float64, device=x.device)
+        nat.check(nat.lib().fgk_spmv_f64(
+            self.n_rows, nat.ptr(self.row_ptr, torch.int64), nat.ptr(self.cols, torch.int32),
+            nat.ptr(self.vals, torch.float64), nat.ptr(x, torch.float64), nat.ptr(y, torch.float64),
+            dev, nat.stream_ptr(self.device)))
+        return y
+
+    def diagonal(self):
+        """the diagonal is the first entry of every row until sort_rows()."""
+        if self.sorted_rows:
+            rows = torch.repeat_interleave(
+                torch.arange(self.row_begin, self.row_end, device=self.cols.device),
+                self.row_ptr[1:] - self.row_ptr[:-1])
+            m = self.cols.long() == rows
+            return self.vals[m]
+        return self.vals[self.row_ptr[:-1]]
+
+    def to_dense(self):
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.cols.device),
+                                       self.row_ptr[1:] - self.row_ptr[:-1])
+        D = torch.zeros(self.n_rows, self.n, dtype=torch.float64, device=self.cols.device)
+        D[rows, self.cols.long()] = self.vals
+        return D
+
+    def to_scipy(self, dtype=np.float64):
+        import scipy.sparse as sp
+        M = sp.csr_matrix((self.vals.cpu().numpy().astype(dtype), self.cols.cpu().numpy(),
+                           self.row_ptr.cpu().numpy()), shape=(self.n_rows, self.n))
+        return M
+
+    def bytes_per_matvec(self, complex_x=False):
+        """algorithmic HBM bytes of one product: 12 B/nnz + 20 (36) B/row."""
+        return 12 * self.nnz + (36 if complex_x else 20) * self.n_rows
+
+
+class BasisIndex:
+    """Device hash index of a packed basis (K4)."""
+
+    def __init__(self, dets):
+        self.dets = dets.contiguous()          # kept alive: the table stores indices into it
+        self.device = dets.device
+        h = C.c_void_p()
+        nat.check(nat.lib().fgk_index_create(
+            nat.ptr(self.dets, torch.int64), self.dets.shape[0], nat.device_index(self.device),
+            nat.stream_ptr(self.device), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                nat.lib().fgk_index_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.dets.shape[0]
+
+    def lookup(self, query):
+        query = query.contiguous()
+        out = torch.empty(query.shape[0], dtype=torch.int32, device=self.device)
+        nat.check(nat.lib().fgk_index_lookup(self._h, nat.ptr(query, torch.int64), query.shape[0],
+                                             nat.ptr(out, torch.int32), nat.stream_ptr(self.device)))
+        return out
+
+    def info(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        nat.check(nat.lib().fgk_index_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(n_dets=a.value, n_alpha_strings=b.value, n_beta_strings=c.value)
+
+
+def sort_unique_dets(dets, n_orb):
+    """Sorted set of packed determinants: ascending (alpha, beta) as unsigned
+    128-bit == the row order of torch.unique(configs, dim=0)
+    (residual_expansion.py:368, skqd.py:942)."""
+    if dets.shape[0] == 0:
+        return dets
+    if n_orb == 64:      # bit 63 in use: map unsigned order onto torch's signed order
+        flip = torch.tensor(-2 ** 63, dtype=torch.int64, device=dets.device)
+        return torch.unique(dets ^ flip, dim=0) ^ flip
+    return torch.unique(dets, dim=0)
+
+
+class MolecularHamiltonian:
+    """Drop-in for reference `MolecularHamiltonian(integrals, device)`
+    (molecular.py:57-61).  `device` must be a CUDA device."""
+
+    def __init__(self, integrals, device: str = "cuda"):
+        self.num_sites = 2 * integrals.n_orbitals          # base.py:21-24
+        self.local_dim = 2
+        self.hilbert_dim = 2 ** self.num_sites
+        self._dev_index = nat.device_index(device)          # raises without CUDA
+        self.device = f"cuda:{self._dev_index}"
+        self.integrals = integrals
+        self.nuclear_repulsion = float(integrals.nuclear_repulsion)
+        self.n_orbitals = int(integrals.n_orbitals)
+        self.n_electrons = int(integrals.n_electrons)
+        self.n_alpha = int(integrals.n_alpha)
+        self.n_beta = int(integrals.n_beta)
+        h1 = np.ascontiguousarray(integrals.h1e, dtype=np.float64)
+        g = np.ascontiguousarray(integrals.h2e, dtype=np.float64)
+        if h1.shape != (self.n_orbitals,) * 2 or g.shape != (self.n_orbitals,) * 4:
+            raise ValueError("integral shapes do not match n_orbitals")
+        # float32 device copies under the reference's attribute names (molecular.py:68-69)
+        self.h1e = torch.from_numpy(h1).float().to(self.device)
+        self.h2e = torch.from_numpy(g).float().to(self.device)
+        self.output_dtype = torch.float64      # set to torch.float32 for reference-typed outputs
+        h = C.c_void_p()
+        nat.check(nat.lib().fgk_ham_create(
+            h1.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), self.n_orbitals,
+            self.n_alpha, self.n_beta, self.nuclear_repulsion, self._dev_index, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                nat.lib().fgk_ham_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- packing (K1) -------------------------------------------------------------
+    def pack(self, configs: torch.Tensor) -> torch.Tensor:
+        """(n, num_sites) 0/1 any dtype/device -> (n, 2) int64 words {alpha, beta} on device."""
+        if configs.dim() == 1:
+            configs = configs.unsqueeze(0)
+        if configs.shape[1] != self.num_sites:
+            raise ValueError(f"configs have {configs.shape[1]} sites, expected {self.num_sites}")
+        c = configs.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty(c.shape[0], 2, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().fgk_pack_i64(nat.ptr(c, torch.int64), c.shape[0], self.n_orbitals,
+                                         nat.ptr(out, torch.int64), self._dev_index,
+                                         nat.stream_ptr(self.device)))
+        return out
+
+    def unpack(self, dets: torch.Tensor, dtype=torch.int64) -> torch.Tensor:
+        dets = dets.contiguous()
+        out = torch.empty(dets.shape[0], self.num_sites, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().fgk_unpack_i64(nat.ptr(dets, torch.int64), dets.shape[0], self.n_orbitals,
+                                           nat.ptr(out, torch.int64), self._dev_index,
+                                           nat.stream_ptr(self.device)))
+        return out if dtype == torch.int64 else out.to(dtype)
+
+    # ---- diagonal (K2) ---------------------------------------------------------------
+    def diag_packed(self, dets):
+        dets = dets.contiguous()
+        out = torch.empty(dets.shape[0], dtype=torch.float64, device=self.device)
+        nat.check(nat.lib().fgk_diag(self._h, nat.ptr(dets, torch.int64), dets.shape[0],
+                                     nat.ptr(out, torch.float64), nat.stream_ptr(self.device)))
+        return out
+
+    @torch.no_grad()
+    def diagonal_elements_batch(self, configs: torch.Tensor) -> torch.Tensor:
+        """molecular.py:133-184.  (batch, num_sites) -> (batch,)."""
+        return self.diag_packed(self.pack(configs)).to(self.output_dtype)
+
+    def diagonal_element(self, config: torch.Tensor) -> torch.Tensor:
+        """molecular.py:186-192."""
+        return self.diagonal_elements_batch(config.unsqueeze(0))[0]
+
+    # ---- connections (K3) --------------------------------------------------------------
+    def connections_packed(self, dets, want_dets=True, want_src=True):
+        """-> (out_dets (N,2) int64, elems (N,) float32, src (N,) int64, offsets (n+1,) int64),
+        connections of dets[j] at offsets[j]:offsets[j+1] in the reference's emission order."""
+        dets = dets.contiguous()
+        n = dets.shape[0]
+        st = nat.stream_ptr(self.device)
+        counts = torch.empty(n, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().fgk_conn_count(self._h, nat.ptr(dets, torch.int64), n,
+                                           nat.ptr(counts, torch.int64), st))
+        offsets = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        total = int(offsets[-1].item()) if n else 0
+        out_dets = torch.empty(total, 2, dtype=torch.int64, device=self.device) if want_dets else None
+        elems = torch.empty(total, dtype=torch.float32, device=self.device)
+        src = torch.empty(total, dtype=torch.int64, device=self.device) if want_src else None
+        if total:
+            nat.check(nat.lib().fgk_conn_fill(
+                self._h, nat.ptr(dets, torch.int64), n, nat.ptr(offsets, torch.int64),
+                nat.ptr(out_dets), nat.ptr(elems, torch.float32), nat.ptr(src), st))
+        return out_dets, elems, src, offsets
+
+    def get_connections(self, config: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """molecular.py:194-327: (connected (N, num_sites) in config's dtype, elements (N,) float32);
+        empty results are shaped tensors (molecular.py:320-321)."""
+        dets = self.pack(config)
+        od, el, _, _ = self.connections_packed(dets, want_src=False)
+        if od.shape[0] == 0:
+            return torch.empty(0, self.num_sites, device=self.device), torch.empty(0, device=self.device)
+        return self.unpack(od, config.dtype), el
+
+    @torch.no_grad()
+    def get_connections_batch(self, configs: torch.Tensor):
+        """The hook utils/connection_cache.py:250-254 looks for (the reference never
+        implements it): (all_connected, all_elements, config_indices)."""
+        if configs.shape[0] == 0:
+            return (torch.empty(0, self.num_sites, device=self.device),
+                    torch.empty(0, device=self.device),
+                    torch.empty(0, dtype=torch.long, device=self.device))
+        od, el, src, _ = self.connections_packed(self.pack(configs))
+        if od.shape[0] == 0:
+            return (torch.empty(0, self.num_sites, device=self.device),
+                    torch.empty(0, device=self.device),
+                    torch.empty(0, dtype=torch.long, device=self.device))
+        return self.unpack(od, configs.dtype), el, src
+
+    def get_all_connections_with_indices(self, configs):
+        """molecular.py:329-377."""
+        return self.get_connections_batch(configs)
+
+    def get_connections_parallel(self, configs, max_workers: int = 8):
+        """molecular.py:518-578 (there: a thread pool with arbitrary completion order;
+        here: one launch, source-ascending order)."""
+        return self.get_connections_batch(configs)
+
+    # ---- projected Hamiltonian (K4 + K5) ---------------------------------------------------
+    def projected_csr(self, basis, mode=nat.H_RAW, row_begin=0, row_end=None, sort_rows=True,
+                      index: Optional[BasisIndex] = None, packed=False) -> ProjectedH:
+        """CSR rows [row_begin,row_end) of <i|H|j> over `basis` (configs, or packed
+        words if packed=True).  mode: H_RAW | H_SYM [| H_DROP_ZEROS]."""
+        dets = basis if packed else self.pack(basis)
+        idx = index if index is not None else BasisIndex(dets)
+        n = len(idx)
+        row_end = n if row_end is None else row_end
+        rows = row_end - row_begin
+        st = nat.stream_ptr(self.device)
+        counts = torch.empty(rows, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().fgk_projh_count(self._h, idx._h, row_begin, row_end, mode,
+                                            nat.ptr(counts, torch.int64), st))
+        row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=row_ptr[1:])
+        nnz = int(row_ptr[-1].item()) if rows else 0
+        cols = torch.empty(nnz, dtype=torch.int32, device=self.device)
+        vals = torch.empty(nnz, dtype=torch.float64, device=self.device)
+        if nnz:
+            nat.check(nat.lib().fgk_projh_fill(self._h, idx._h, row_begin, row_end, mode,
+                                               nat.ptr(row_ptr, torch.int64),
+                                               nat.ptr(cols, torch.int32),
+                                               nat.ptr(vals, torch.float64), st))
+        P = ProjectedH(n, row_ptr, cols, vals, self.device, row_begin, row_end, mode)
+        P._index = idx
+        return P.sort_rows() if sort_rows else P
+
+    @torch.no_grad()
+    def matrix_elements_fast(self, configs: torch.Tensor) -> torch.Tensor:
+        """molecular.py:471-516: dense (n, n), H[i, j] = <i|H|j> raw directed."""
+        if configs.shape[0] == 0:
+            return torch.zeros(0, 0, dtype=self.output_dtype, device=self.device)
+        return self.projected_csr(configs, nat.H_RAW, sort_rows=False).to_dense().to(self.output_dtype)
+
+    def matrix_elements(self, configs_bra: torch.Tensor, configs_ket: torch.Tensor) -> torch.Tensor:
+        """molecular.py:640-685."""
+        if configs_bra.shape == configs_ket.shape and bool(
+                torch.all(configs_bra.to(self.device) == configs_ket.to(self.device))):
+            return self.matrix_elements_fast(configs_bra)
+        bra = self.pack(configs_bra)
+        ket = self.pack(configs_ket)
+        idx = BasisIndex(bra)
+        H = torch.zeros(bra.shape[0], ket.shape[0], dtype=torch.float64, device=self.device)
+        hit = idx.lookup(ket).long()                       # diagonal, :671-674
+        kk = torch.nonzero(hit >= 0).squeeze(1)
+        if kk.numel():
+            H[hit[kk], kk] = self.diag_packed(ket[kk])
+        od, el, src, _ = self.connections_packed(ket)      # off-diagonal, :677-683
+        if od.shape[0]:
+            i = idx.lookup(od).long()
+            m = i >= 0
+            H[i[m], src[m]] = el[m].double()
+        return H.to(self.output_dtype)
+
+    @torch.no_grad()
+    def get_sparse_matrix_elements(self, configs: torch.Tensor):
+        """molecular.py:580-638: COO (rows, cols, values) of the OFF-diagonal hits,
+        j ascending, emission order inside j."""
+        if configs.shape[0] == 0:
+            return (torch.tensor([], dtype=torch.long, device=self.device),
+                    torch.tensor([], dtype=torch.long, device=self.device),
+                    torch.tensor([], dtype=torch.float32, device=self.device))
+        dets = self.pack(configs)
+        idx = BasisIndex(dets)
+        od, el, src, _ = self.connections_packed(dets)
+        i = idx.lookup(od).long() if od.shape[0] else torch.empty(0, dtype=torch.long, device=self.device)
+        m = i >= 0
+        return i[m], src[m], el[m]
+
+    # ---- misc reference API -------------------------------------------------------------------
+    def get_hf_state(self) -> torch.Tensor:
+        """molecular.py:778-792."""
+        config = torch.zeros(self.num_sites, dtype=torch.long, device=self.device)
+        config[: self.n_alpha] = 1
+        config[self.n_orbitals: self.n_orbitals + self.n_beta] = 1
+        return config
+
+    def _config_to_index(self, config: torch.Tensor) -> int:
+        """base.py: big-endian integer of the configuration."""
+        idx = 0
+        for b in config.tolist():
+            idx = (idx << 1) | int(b)
+        return idx
+
+    def fci_dets(self) -> torch.Tensor:
+        """all C(n,na)*C(n,nb) determinants, packed, in the reference's order
+        (itertools.combinations, alpha-major: skqd.py:155-169, molecular.py:894-905)."""
+        n = self.n_orbitals
+
+        def strings(k):
+            out = np.zeros(comb(n, k), dtype=np.uint64)
+            for i, occ in enumerate(combinations(range(n), k)):
+                w = 0
+                for p in occ:
+                    w |= 1 << (n - 1 - p)
+                out[i] = w
+            return out
+
+        a, b = strings(self.n_alpha), strings(self.n_beta)
+        dets = np.empty((len(a), len(b), 2), dtype=np.uint64)
+        dets[:, :, 0] = a[:, None]
+        dets[:, :, 1] = b[None, :]
+        return torch.from_numpy(dets.reshape(-1, 2).view(np.int64)).to(self.device)
+
+    def fci_energy(self) -> float:
+        """molecular.py:872-942: lowest eigenvalue of the symmetrised projected H over
+        the full particle-conserving space."""
+        from .solvers import lowest_eigenpairs
+        dets = self.fci_dets()
+        P = self.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)
+        w, _ = lowest_eigenpairs(P, k=1)
+        return float(w[0])

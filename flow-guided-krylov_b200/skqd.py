@@ -1,0 +1,314 @@
+"""Stage-4 sample-based Krylov quantum diagonalisation over the sm_100a engine.
+
+Host-side mirror of reference src/krylov/skqd.py for MOLECULAR Hamiltonians:
+  SKQDConfig (:48-72), SampleBasedKrylovDiagonalization (:75-888, molecular
+  branches only), FlowGuidedSKQD (:891-1059) -- same constructor / method
+  signatures and the same result dictionaries.
+
+What changed underneath:
+  * the particle-conserving subspace is a packed determinant array + device hash
+    index instead of a Python list + tuple dict (:135-177);
+  * the subspace Hamiltonian is a device CSR built by fgk_projh_* (:374-419),
+    raw directed elements, exactly the reference's (row=i, col=j) entries;
+  * |psi> lives in the subspace as a complex128 device vector (the reference
+    round-trips a 2^num_sites dense vector, :298-321, :608-614);
+  * exp(-i dt H)|psi> is a Taylor series over fgk_spmv_z (:291-293);
+  * projected ground-state problems use the symmetrised device CSR + solvers
+    (:683-807), never a dense float32 n x n matrix.
+The Trotter / Pauli / spin-lattice branches (:421-536) are out of scope.
+"""
+from dataclasses import dataclass
+from math import comb
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .hamiltonian import BasisIndex, sort_unique_dets
+from .solvers import expm_multiply, lowest_eigenpairs, DENSE_EIG_MAX
+
+try:
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(x, **k):
+        return x
+
+
+@dataclass
+class SKQDConfig:
+    """skqd.py:48-72 (field for field) + one engine knob."""
+    max_krylov_dim: int = 12
+    time_step: float = 0.1
+    total_evolution_time: Optional[float] = None
+    num_trotter_steps: int = 8
+    shots_per_krylov: int = 100000
+    use_cumulative_basis: bool = True
+    num_eigenvalues: int = 2
+    which_eigenvalues: str = "SA"
+    regularization: float = 1e-8
+    use_gpu: bool = True
+    # True reproduces the value the reference's scipy path returns (SURVEY F5:
+    # eigsh(k=2,'SA',return_eigenvectors=False)[0] is lambda_1 for n >= 100);
+    # False always returns lambda_0.
+    reference_compat: bool = True
+
+
+class SampleBasedKrylovDiagonalization:
+    """skqd.py:75-888 for Hamiltonians with n_alpha / n_beta (molecular)."""
+
+    MAX_SUBSPACE = 50_000_000
+
+    def __init__(self, hamiltonian, config: Optional[SKQDConfig] = None,
+                 initial_state: Optional[torch.Tensor] = None):
+        self.hamiltonian = hamiltonian
+        self.config = config or SKQDConfig()
+        self.num_sites = hamiltonian.num_sites
+        self._is_molecular = hasattr(hamiltonian, "n_alpha") and hasattr(hamiltonian, "n_beta")
+        if not self._is_molecular:
+            raise NotImplementedError(
+                "flow_guided_krylov_b200 covers the molecular SKQD path only "
+                "(spin-lattice / Trotter branches of skqd.py:421-536 are out of scope)")
+        self._subspace_dets = None
+        self._subspace_index = None
+        self._subspace_H = None
+        self._setup_particle_conserving_subspace()
+        self.initial_state = initial_state if initial_state is not None else hamiltonian.get_hf_state()
+        if self.config.total_evolution_time is not None:                     # :123-128
+            self.time_step = self.config.total_evolution_time / self.config.num_trotter_steps
+        else:
+            self.time_step = self.config.time_step
+        self.krylov_samples: List[Dict[str, int]] = []
+        self.krylov_sample_dets: List[torch.Tensor] = []   # packed, ascending key, per step
+        self.krylov_states: List[torch.Tensor] = []        # subspace amplitudes per step
+        self.cumulative_basis: List[torch.Tensor] = []
+        self.energies: List[float] = []
+
+    @property
+    def device(self) -> torch.device:
+        return torch.device(self.hamiltonian.device)
+
+    # :135-177
+    def _setup_particle_conserving_subspace(self):
+        H = self.hamiltonian
+        n_valid = comb(H.n_orbitals, H.n_alpha) * comb(H.n_orbitals, H.n_beta)
+        if n_valid > self.MAX_SUBSPACE:
+            raise ValueError(
+                f"particle-conserving subspace has {n_valid:,} determinants; full-space SKQD "
+                "time evolution is not feasible (the reference enumerates the same space)")
+        self._subspace_dets = H.fci_dets()
+        self._subspace_index = BasisIndex(self._subspace_dets)
+
+    @property
+    def _subspace_basis(self):
+        """(N_fci, num_sites) int64 configurations (compat with skqd.py:169)."""
+        return self.hamiltonian.unpack(self._subspace_dets)
+
+    # :374-419
+    def _build_subspace_hamiltonian(self):
+        if self._subspace_H is None:
+            self._subspace_H = self.hamiltonian.projected_csr(
+                self._subspace_dets, nat.H_RAW, index=self._subspace_index, packed=True)
+        return self._subspace_H
+
+    def _build_sparse_hamiltonian(self):
+        return self._build_subspace_hamiltonian()
+
+    # :275-296 (in the subspace; one step = one expm_multiply)
+    def _evolve_subspace(self, psi: torch.Tensor, num_steps: int = 1) -> torch.Tensor:
+        P = self._build_subspace_hamiltonian()
+        if not hasattr(self, "_expm_cache"):
+            from .solvers import one_norm
+            d = P.diagonal()
+            mu = float(d.sum()) / P.n
+            cs = one_norm(P) - d.abs() + (d - mu).abs()
+            self._expm_cache = (mu, float(cs.max()))
+        mu, nrm = self._expm_cache
+        for _ in range(num_steps):
+            psi = expm_multiply(P, psi, -1j * self.time_step, mu=mu, norm1=nrm)
+        return psi
+
+    def _subspace_position(self, config: torch.Tensor) -> int:
+        d = self.hamiltonian.pack(config.to(self.device))
+        pos = int(self._subspace_index.lookup(d)[0].item())
+        if pos < 0:
+            raise ValueError("initial state is not in the particle-conserving subspace")
+        return pos
+
+    # :538-571 (sampling over the subspace amplitudes)
+    def _sample_from_state(self, psi: torch.Tensor, num_samples: int):
+        probs = psi.abs() ** 2
+        probs = probs / probs.sum()
+        idx = torch.multinomial(probs, num_samples, replacement=True)
+        uniq, counts = torch.unique(idx, return_counts=True)
+        dets = self._subspace_dets[uniq]
+        # ascending Hilbert index == ascending key (np.unique order of the reference, :563)
+        from .expansion import _key_sort_order
+        o = _key_sort_order(dets, self.hamiltonian.n_orbitals)
+        return dets[o], counts[o]
+
+    def _dets_to_bitstrings(self, dets):
+        cfg = self.hamiltonian.unpack(dets).cpu().numpy().astype(np.uint8)
+        return ["".join("1" if b else "0" for b in row) for row in cfg]
+
+    # :581-635
+    def generate_krylov_samples(self, max_krylov_dim: Optional[int] = None, progress: bool = True):
+        if max_krylov_dim is None:
+            max_krylov_dim = self.config.max_krylov_dim
+        self.krylov_samples, self.krylov_sample_dets, self.krylov_states = [], [], []
+        n = self._subspace_dets.shape[0]
+        psi = torch.zeros(n, dtype=torch.complex128, device=self.device)
+        psi[self._subspace_position(self.initial_state)] = 1.0
+        it = range(max_krylov_dim)
+        if progress:
+            it = tqdm(it, desc="Generating Krylov states")
+        for k in it:
+            dets, counts = self._sample_from_state(psi, self.config.shots_per_krylov)
+            self.krylov_sample_dets.append(dets)
+            self.krylov_samples.append(dict(zip(self._dets_to_bitstrings(dets), counts.tolist())))
+            self.krylov_states.append(psi)
+            if k < max_krylov_dim - 1:
+                psi = self._evolve_subspace(psi, 1)
+        return self.krylov_samples
+
+    def set_krylov_samples(self, sample_configs: List[torch.Tensor]):
+        """Inject externally drawn samples (e.g. the reference's own bitstring sets, the
+        parity protocol of SURVEY 8d): one (n_k, num_sites) tensor per Krylov step."""
+        self.krylov_sample_dets = [self.hamiltonian.pack(c) for c in sample_configs]
+        self.krylov_samples = [dict.fromkeys(self._dets_to_bitstrings(d), 1)
+                               for d in self.krylov_sample_dets]
+
+    # :637-656
+    def build_cumulative_basis(self):
+        cumulative, allsamp = [], {}
+        for samples in self.krylov_samples:
+            for bs, c in samples.items():
+                allsamp[bs] = allsamp.get(bs, 0) + c
+            cumulative.append(dict(allsamp))
+        return cumulative
+
+    def _basis_dets(self, krylov_index: int, cumulative: bool = True):
+        """packed basis in the reference's insertion order (dict order, :678)."""
+        if not cumulative:
+            return self.krylov_sample_dets[krylov_index]
+        allk = torch.cat(self.krylov_sample_dets[: krylov_index + 1], dim=0)
+        # first-occurrence order == dict insertion order of build_cumulative_basis
+        uniq, inv = torch.unique(allk, dim=0, return_inverse=True)
+        first = torch.full((uniq.shape[0],), allk.shape[0], dtype=torch.long, device=allk.device)
+        first.scatter_reduce_(0, inv, torch.arange(allk.shape[0], device=allk.device), reduce="amin")
+        return allk[torch.sort(first).values]
+
+    # :658-681
+    def get_basis_states(self, krylov_index: int, cumulative: bool = True) -> torch.Tensor:
+        return self.hamiltonian.unpack(self._basis_dets(krylov_index, cumulative))
+
+    # :683-807
+    def compute_ground_state_energy(self, basis: Optional[torch.Tensor] = None,
+                                    return_eigenvector: bool = False,
+                                    regularization: float = 1e-8):
+        if basis is None:
+            dets = self._basis_dets(len(self.krylov_samples) - 1)
+        else:
+            dets = self.hamiltonian.pack(basis.to(self.device))
+        return self._ground_state_packed(dets, return_eigenvector, regularization)
+
+    def _ground_state_packed(self, dets, return_eigenvector=False, regularization=1e-8):
+        P = self.hamiltonian.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)   # :718-734
+        n = P.n
+        reg = regularization if regularization > 0 else 0.0                                 # :738-739
+        if n <= DENSE_EIG_MAX:
+            D = P.to_dense()
+            D = 0.5 * (D + D.T) + reg * torch.eye(n, dtype=torch.float64, device=D.device)
+            w, v = torch.linalg.eigh(D)
+            aw = w.abs()
+            cond = float(aw.max() / aw.min()) if float(aw.min()) > 0 else float("inf")      # :743
+            if cond > 1e12:                                                                 # :744-750
+                thr = 1e-10 * float(aw.max())
+                s_reg = torch.where(aw > thr, aw, torch.full_like(aw, thr))
+                w2 = torch.sign(w) * s_reg
+                w2 = torch.where(w == 0, s_reg, w2)
+                Hreg = (v * w2) @ v.T
+                w, v = torch.linalg.eigh(0.5 * (Hreg + Hreg.T))
+                return float(w[0]), (v[:, 0].cpu() if return_eigenvector else None)
+        else:
+            k = min(self.config.num_eigenvalues, n - 1)
+            w, v = lowest_eigenpairs(P, k=k)
+            w = w + reg
+        if n < 100 or return_eigenvector or not self.config.reference_compat:               # :754-758,:790-793
+            E0 = float(w[0])
+        else:                                                                               # :794-796, SURVEY F5
+            E0 = float(w[min(self.config.num_eigenvalues, n - 1) - 1])
+        return E0, (v[:, 0].cpu() if return_eigenvector else None)
+
+    # :845-888
+    def run(self, max_krylov_dim: Optional[int] = None, progress: bool = True):
+        if max_krylov_dim is None:
+            max_krylov_dim = self.config.max_krylov_dim
+        self.generate_krylov_samples(max_krylov_dim, progress=progress)
+        results = {"krylov_dims": [], "energies": [], "basis_sizes": []}
+        for k in range(1, max_krylov_dim):
+            dets = self._basis_dets(k, True)
+            E0, _ = self._ground_state_packed(dets)
+            results["krylov_dims"].append(k + 1)
+            results["energies"].append(E0)
+            results["basis_sizes"].append(int(dets.shape[0]))
+        self.energies = results["energies"]
+        return results
+
+
+class FlowGuidedSKQD(SampleBasedKrylovDiagonalization):
+    """skqd.py:891-1059, same signatures and result keys."""
+
+    def __init__(self, hamiltonian, nf_basis: torch.Tensor, config: Optional[SKQDConfig] = None,
+                 initial_state: Optional[torch.Tensor] = None):
+        super().__init__(hamiltonian, config, initial_state)
+        self.nf_basis = nf_basis
+
+    def _combined_dets(self, krylov_index: int, include_nf: bool = True):
+        kd = self._basis_dets(krylov_index, True)
+        if not include_nf:
+            return kd
+        nf = self.hamiltonian.pack(self.nf_basis.to(self.device))
+        return sort_unique_dets(torch.cat([nf, kd], dim=0), self.hamiltonian.n_orbitals)   # :939-942
+
+    # :914-944
+    def get_combined_basis(self, krylov_index: int, include_nf: bool = True) -> torch.Tensor:
+        return self.hamiltonian.unpack(self._combined_dets(krylov_index, include_nf))
+
+    # :946-1059
+    def run_with_nf(self, max_krylov_dim: Optional[int] = None, progress: bool = True,
+                    regenerate_samples: bool = True):
+        if max_krylov_dim is None:
+            max_krylov_dim = self.config.max_krylov_dim
+        reg = self.config.regularization
+        nf_dets = self.hamiltonian.pack(self.nf_basis.to(self.device))
+        E_nf, _ = self._ground_state_packed(nf_dets, regularization=reg)                   # :974-977
+        if regenerate_samples or not self.krylov_sample_dets:
+            self.generate_krylov_samples(max_krylov_dim, progress=progress)                # :981
+        results = {
+            "krylov_dims": [], "energies_krylov": [], "energies_combined": [],
+            "basis_sizes_krylov": [], "basis_sizes_combined": [], "energy_nf_only": E_nf,
+            "nf_basis_size": len(self.nf_basis), "numerical_warnings": []}
+        best_energy = E_nf
+        for k in range(1, max_krylov_dim):
+            kd = self._basis_dets(k, True)
+            E_k, _ = self._ground_state_packed(kd, regularization=reg)                     # :1001-1004
+            cd = self._combined_dets(k, True)
+            E_c, _ = self._ground_state_packed(cd, regularization=reg)                     # :1007-1011
+            if k > 1 and results["energies_combined"]:                                     # :1015-1031
+                change = E_c - results["energies_combined"][-1]
+                if change > 0.001:
+                    results["numerical_warnings"].append(
+                        f"k={k+1}: Energy increased by {change*1000:.4f} mHa (numerical instability)")
+                if abs(change) > 1.0:
+                    results["numerical_warnings"].append(
+                        f"k={k+1}: Large energy jump {abs(change):.4f} Ha")
+            if E_c < best_energy:                                                          # :1034-1036
+                best_energy = E_c
+            results["krylov_dims"].append(k + 1)
+            results["energies_krylov"].append(E_k)
+            results["energies_combined"].append(E_c)
+            results["basis_sizes_krylov"].append(int(kd.shape[0]))
+            results["basis_sizes_combined"].append(int(cd.shape[0]))
+        results["best_stable_energy"] = best_energy                                        # :1055-1057
+        return results

@@ -1,0 +1,152 @@
+"""Krylov drivers over the device SpMV (K6/K10).
+
+* lowest_eigenpairs -- replaces np.linalg.eigh / scipy eigsh(which='SA') in
+  residual_expansion.py:408-443, skqd.py:754-796, molecular.py:929-937.
+  Small problems: dense torch.linalg.eigh on the device (cuSOLVER) -- the only
+  dense step of the path.  Large problems: block Davidson with the diagonal
+  preconditioner, H.v by fgk_spmv_f64.
+* expm_multiply -- replaces scipy.sparse.linalg.expm_multiply(-i dt H, psi)
+  (skqd.py:291-293): scaled, shifted Taylor series in complex128 with the
+  Al-Mohy--Higham truncation test (tol 2^-53), H.v by fgk_spmv_z.
+Vectors stay on the device; only scalars (norms, small projected matrices) are
+looked at on the host.
+"""
+import math
+
+import torch
+
+DENSE_EIG_MAX = 3072
+
+
+def _full_matvec(P, x):
+    if P.row_begin != 0 or P.row_end != P.n:
+        raise ValueError("solver needs the full row range (use dist.ShardedH for row blocks)")
+    return P.matvec(x)
+
+
+def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=400, max_space=None, matvec=None,
+                      diagonal=None, dense_max=DENSE_EIG_MAX, v0=None):
+    """k lowest eigenpairs of the symmetric operator P (a ProjectedH built with
+    H_SYM, or any object with .n plus `matvec`/`diagonal` callables).
+    Returns (w (k,) float64 tensor ascending, V (n,k))."""
+    n = P.n
+    mv = matvec if matvec is not None else (lambda x: _full_matvec(P, x))
+    k = min(k, n)
+    if n <= dense_max and matvec is None:
+        D = P.to_dense()
+        w, v = torch.linalg.eigh(0.5 * (D + D.T))
+        return w[:k].clone(), v[:, :k].clone()
+    diag = diagonal if diagonal is not None else P.diagonal()
+    dev = diag.device
+    nb = min(max(2 * k, k + 2), n)                 # initial block: lowest diagonal entries
+    if max_space is None:
+        max_space = max(8 * k, 24)
+    V = torch.zeros(n, nb, dtype=torch.float64, device=dev)
+    start = torch.argsort(diag)[:nb]
+    V[start, torch.arange(nb, device=dev)] = 1.0
+    if v0 is not None:
+        V[:, 0] = v0.to(dev, torch.float64)
+        V, _ = torch.linalg.qr(V)
+    W = torch.stack([mv(V[:, i].contiguous()) for i in range(V.shape[1])], dim=1)
+    w = X = None
+    for _ in range(max_iter):
+        T = V.T @ W
+        T = 0.5 * (T + T.T)
+        th, s = torch.linalg.eigh(T)
+        th, s = th[:k], s[:, :k]
+        X = V @ s
+        R = W @ s - X * th
+        rn = torch.linalg.norm(R, dim=0)
+        w = th
+        scale = max(1.0, float(th.abs().max()))
+        if float(rn.max()) < tol * scale:
+            break
+        # Davidson correction with the diagonal preconditioner
+        new = []
+        for i in range(k):
+            if float(rn[i]) < tol * scale:
+                continue
+            den = th[i] - diag
+            den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
+            new.append(R[:, i] / den)
+        if V.shape[1] + len(new) > max_space:       # thick restart on the Ritz vectors
+            V = X.clone()
+            V, _ = torch.linalg.qr(V)
+            W = torch.stack([mv(V[:, i].contiguous()) for i in range(V.shape[1])], dim=1)
+        added = []
+        for t in new:
+            for _ in range(2):                       # CGS2
+                t = t - V @ (V.T @ t)
+                for a in added:
+                    t = t - a * torch.dot(a, t)
+            nt = float(torch.linalg.norm(t))
+            if nt > 1e-10:
+                added.append(t / nt)
+        if not added:
+            break
+        A = torch.stack(added, dim=1)
+        V = torch.cat([V, A], dim=1)
+        W = torch.cat([W, torch.stack([mv(A[:, i].contiguous()) for i in range(A.shape[1])], dim=1)], dim=1)
+    return w.clone(), X.clone()
+
+
+# Al-Mohy & Higham 2011, table 3.1 (tol = 2^-53): theta_m for selected m
+_THETA = {1: 2.29e-16, 2: 2.58e-8, 3: 1.39e-5, 4: 3.40e-4, 5: 2.40e-3, 6: 9.07e-3, 7: 2.38e-2,
+          8: 5.00e-2, 9: 8.96e-2, 10: 1.44e-1, 11: 2.14e-1, 12: 3.00e-1, 13: 4.00e-1, 14: 5.14e-1,
+          15: 6.41e-1, 16: 7.81e-1, 17: 9.31e-1, 18: 1.09, 19: 1.26, 20: 1.44, 21: 1.62, 22: 1.82,
+          23: 2.01, 24: 2.22, 25: 2.43, 26: 2.64, 27: 2.86, 28: 3.08, 29: 3.31, 30: 3.54, 35: 4.7,
+          40: 6.0, 45: 7.2, 50: 8.5, 55: 9.9}
+
+
+def one_norm(P):
+    """exact ||H||_1 = max column abs sum of a CSR operator (device scatter-add)."""
+    cs = torch.zeros(P.n, dtype=torch.float64, device=P.vals.device)
+    cs.index_add_(0, P.cols.long(), P.vals.abs())
+    return cs
+
+
+def expm_multiply(P, psi, t, matvec=None, mu=None, norm1=None, allreduce_max=None):
+    """exp(t * H) psi for a real CSR operator H and complex scalar t (t = -i dt in
+    SKQD, skqd.py:291).  Shift by mu = trace(H)/n, scale by s, Taylor degree m*
+    chosen to minimise m * ceil(|t| ||H - mu||_1 / theta_m); early exit when two
+    successive terms fall under 2^-53 relative to the running sum."""
+    mv = matvec if matvec is not None else (lambda x: _full_matvec(P, x))
+    n = P.n
+    psi = psi.to(torch.complex128)
+    if mu is None:
+        mu = float(P.diagonal().sum()) / n
+    if norm1 is None:
+        d = P.diagonal()
+        cs = one_norm(P) - d.abs() + (d - mu).abs()       # ||H - mu I||_1, exact
+        norm1 = float(cs.max())
+    a = abs(t) * norm1
+    tol = 2.0 ** -53
+    if a == 0.0:
+        m_star, s = 1, 1
+    else:
+        best = None
+        for m, th in _THETA.items():
+            cost = m * max(1, math.ceil(a / th))
+            if best is None or cost < best[0]:
+                best = (cost, m, max(1, math.ceil(a / th)))
+        _, m_star, s = best
+    eta = complex(math.e) ** (t * mu / s)
+    F = psi.clone()
+    B = psi.clone()
+
+    def inf_norm(v):
+        x = float(v.abs().max()) if v.numel() else 0.0
+        return allreduce_max(x) if allreduce_max is not None else x
+
+    for _ in range(s):
+        c1 = inf_norm(B)
+        for j in range(1, m_star + 1):
+            B = (mv(B) - mu * B) * (t / (s * j))
+            c2 = inf_norm(B)
+            F = F + B
+            if c1 + c2 <= tol * inf_norm(F):
+                break
+            c1 = c2
+        F = F * eta
+        B = F.clone()
+    return F

@@ -1,0 +1,170 @@
+/*
+ * fgk_b200.h -- C ABI of the B200-native determinant-space Hamiltonian engine.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * George930502/Flow-Guided-Krylov.  The reference is pure
+ * Python and has no FFI of its own; each entry point below names the reference
+ * method (file:line under reference/src) whose work it takes over.  The
+ * reference-side binding (ctypes, because the reference host language is
+ * Python) is shown in INTEGRATION.md and implemented in
+ * flow-guided-krylov_b200/_native.py.
+ *
+ * Rules of the boundary
+ *   - plain C: pointers, sizes, ints.  No torch/C++ types.
+ *   - every function returns 0 (FGK_OK) or a negative error code;
+ *     fgk_last_error() gives the thread-local message.  No exceptions cross.
+ *   - the CALLER allocates every buffer (device memory unless a parameter is
+ *     documented "host"); variable-size outputs are two-phase: count -> fill.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all work is enqueued on it and the call returns without synchronising
+ *     unless documented otherwise.
+ *   - handles are opaque and immutable after creation: concurrent calls on
+ *     different streams are safe (the reference calls get_connections from an
+ *     8-thread pool, molecular.py:554).
+ *   - a determinant is two uint64 words {alpha, beta}; orbital p of a spin block
+ *     is bit (n_orb-1-p).  Sorting (alpha, beta) as a 128-bit unsigned number
+ *     reproduces the reference's site-0-is-MSB key order (molecular.py:498-500).
+ *     n_orb <= 64.  Arrays of determinants are uint64[n][2], 16-byte aligned.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     FGK_ERR_CUDA.
+ */
+#ifndef FGK_B200_H
+#define FGK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGK_OK 0
+#define FGK_ERR_ARG (-1)         /* bad argument                                   */
+#define FGK_ERR_CUDA (-2)        /* CUDA runtime error (message has the detail)    */
+#define FGK_ERR_CAPACITY (-3)    /* a caller-sized workspace overflowed            */
+#define FGK_ERR_UNSUPPORTED (-4) /* e.g. n_orb > 64                                */
+
+/* projected-H flavours */
+#define FGK_H_RAW 0        /* <i|H|j> exactly as get_connections(j) reports it      */
+#define FGK_H_SYM 1        /* 0.5*(<i|H|j> + <j|H|i>)  (residual_expansion.py:425,  */
+                           /*  skqd.py:725, molecular.py:921)                       */
+#define FGK_H_DROP_ZEROS 2 /* OR-able: skip entries whose value is exactly 0.0      */
+                           /*  (what scipy csr_matrix(dense) does, skqd.py:783)     */
+
+/* PT2 accumulation flavours */
+#define FGK_PT2_SUM 0      /* signed coupling sum   (residual_expansion.py:515-520) */
+#define FGK_PT2_MAXABS 1   /* max |c_j * elem|      (residual_expansion.py:218-236) */
+
+typedef struct fgk_ham* fgk_ham_t;
+typedef struct fgk_index* fgk_index_t;
+typedef struct fgk_pt2* fgk_pt2_t;
+
+int fgk_version(void);
+const char* fgk_last_error(void);
+/* sm count, L2 bytes, free and total HBM bytes of `device` (host outputs) */
+int fgk_device_info(int device, int* sm_count, size_t* l2_bytes, size_t* free_bytes,
+                    size_t* total_bytes);
+
+/* ---- Hamiltonian handle ------------------------------------------------------
+ * replaces MolecularHamiltonian.__init__ + _precompute_vectorized_integrals +
+ * _precompute_single_excitation_data (molecular.py:57-117).
+ * h1 (n,n) and g (n,n,n,n), chemist order (pq|rs), are HOST FP64 arrays; they are
+ * rounded to float32 exactly like the reference's .float() (molecular.py:68-69). */
+int fgk_ham_create(const double* h1_host, const double* g_host, int n_orb, int n_alpha,
+                   int n_beta, double e_nuc, int device, fgk_ham_t* out);
+int fgk_ham_destroy(fgk_ham_t h);
+
+/* ---- K1 pack / unpack --------------------------------------------------------
+ * replaces the integer-key encoders molecular.py:498-500,609-611 and
+ * connection_cache.py:82-98.  cfg is (n, 2*n_orb) int64 0/1, row-major. */
+int fgk_pack_i64(const int64_t* cfg, int64_t n, int n_orb, uint64_t* dets, int device, void* stream);
+int fgk_unpack_i64(const uint64_t* dets, int64_t n, int n_orb, int64_t* cfg, int device, void* stream);
+
+/* ---- K2 diagonal ---------------------------------------------------------------
+ * replaces diagonal_elements_batch / diagonal_element (molecular.py:133-192).
+ * FP64 arithmetic on the float32-rounded tables. */
+int fgk_diag(fgk_ham_t h, const uint64_t* dets, int64_t n, double* out, void* stream);
+
+/* ---- K3 connections, reference emission order ---------------------------------
+ * replaces get_connections (molecular.py:194-327) and its batch wrappers
+ * get_all_connections_with_indices (:329-377), get_connections_parallel (:518-578)
+ * and the unimplemented get_connections_batch hook (utils/connection_cache.py:250).
+ * counts[j] = number of connections of dets[j].  offsets = exclusive scan of counts
+ * (n+1 entries).  Outputs: out_dets (total,2) u64, out_elems float32 (exact
+ * reference values), out_src int64 (index j of the source), any of which may be NULL. */
+int fgk_conn_count(fgk_ham_t h, const uint64_t* dets, int64_t n, int64_t* counts, void* stream);
+int fgk_conn_fill(fgk_ham_t h, const uint64_t* dets, int64_t n, const int64_t* offsets,
+                  uint64_t* out_dets, float* out_elems, int64_t* out_src, void* stream);
+
+/* ---- K4 basis index -------------------------------------------------------------
+ * replaces the Python dict / set lookups molecular.py:501,512;
+ * residual_expansion.py:445-449,513; skqd.py:171-175,405-407.
+ * `dets` must stay alive and unchanged while the index is used (the table stores
+ * indices into it).  Duplicate determinants resolve to the LAST index, like the
+ * reference's dict comprehension.  Synchronises `stream` once (to size the
+ * alpha/beta string sets). */
+int fgk_index_create(const uint64_t* dets, int64_t n, int device, void* stream, fgk_index_t* out);
+int fgk_index_destroy(fgk_index_t idx);
+/* out_idx[k] = position of query[k] in the basis, or -1 */
+int fgk_index_lookup(fgk_index_t idx, const uint64_t* query, int64_t m, int32_t* out_idx, void* stream);
+/* number of distinct alpha / beta strings of the basis (host outputs) */
+int fgk_index_info(fgk_index_t idx, int64_t* n_dets, int64_t* n_alpha_strings, int64_t* n_beta_strings);
+
+/* ---- K5 projected Hamiltonian (CSR rows) ------------------------------------------
+ * replaces matrix_elements_fast (molecular.py:471-516), get_sparse_matrix_elements
+ * (:580-638) and _build_subspace_hamiltonian (skqd.py:374-419).
+ * Rows [row_begin,row_end) of H over the indexed basis; entry (i,j) = <i|H|j>;
+ * the diagonal is always stored first in its row.  counts has row_end-row_begin
+ * entries; row_ptr = exclusive scan (local, starts at 0).  cols are GLOBAL basis
+ * indices.  Entries of a row are in enumeration order; fgk_csr_sort_rows orders
+ * them by column. */
+int fgk_projh_count(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end, int mode,
+                    int64_t* counts, void* stream);
+int fgk_projh_fill(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end, int mode,
+                   const int64_t* row_ptr, int32_t* cols, double* vals, void* stream);
+int fgk_csr_sort_rows(int64_t n_rows, const int64_t* row_ptr, int32_t* cols, double* vals,
+                      int device, void* stream);
+
+/* ---- K6 sparse H.v, FP64 CSR ----------------------------------------------------------
+ * replaces scipy's csr_matvec inside eigsh (skqd.py:784, residual_expansion.py:435,
+ * molecular.py:936) and inside expm_multiply (skqd.py:291-293).
+ * y[i] = sum_k vals[k] * x[cols[k]].  _z: x, y complex128 interleaved (re,im), H real. */
+int fgk_spmv_f64(int64_t n_rows, const int64_t* row_ptr, const int32_t* cols, const double* vals,
+                 const double* x, double* y, int device, void* stream);
+int fgk_spmv_z(int64_t n_rows, const int64_t* row_ptr, const int32_t* cols, const double* vals,
+               const double* x, double* y, int device, void* stream);
+
+/* ---- K7/K8 PT2 residual expansion --------------------------------------------------------
+ * replaces SelectedCIExpander._find_important_configs (residual_expansion.py:451-554)
+ * and ResidualBasedExpander._find_residual_configs (:174-253).
+ * The workspace is a device hash map determinant -> FP64 accumulator with room for
+ * `capacity` distinct candidates. */
+int fgk_pt2_create(int64_t capacity, int device, fgk_pt2_t* out);
+int fgk_pt2_destroy(fgk_pt2_t ws);
+int fgk_pt2_reset(fgk_pt2_t ws, void* stream);
+/* For every source s in [0,n_src): j = src_idx[s] (basis position), coefficient
+ * coeff[s]; every connection x of basis[j] with x not in the basis adds
+ * coeff[s]*<x|H|j> to x's accumulator (mode SUM) or maxes |.| (mode MAXABS).
+ * Only candidates with (hash(x) >> 40) % n_pass == pass_id are handled, so that a
+ * candidate set larger than the workspace can be processed exactly in n_pass
+ * sweeps.  Overflow is reported by fgk_pt2_count. */
+int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, const int64_t* src_idx,
+                       const double* coeff, int64_t n_src, int mode, int n_pass, int pass_id,
+                       void* stream);
+/* merge externally produced (determinant, value) pairs (multi-GPU dedup exchange) */
+int fgk_pt2_merge(fgk_pt2_t ws, const uint64_t* dets, const double* vals, int64_t m, int mode,
+                  void* stream);
+/* synchronises; host outputs: number of pool slots used (incl. dead ones), raw
+ * candidates tested so far, overflow flag.  Returns FGK_ERR_CAPACITY on overflow. */
+int fgk_pt2_count(fgk_pt2_t ws, void* stream, int64_t* n_slots, int64_t* n_raw, int* overflow);
+/* for slot k in [0,n_slots): out_dets[k], out_coupling[k]; dead slots get
+ * out_valid[k] = 0.  If h != NULL also out_diag[k] = <x|H|x> and
+ * out_importance[k] = coupling^2 / (|energy - diag| + 1e-10)  (:547-548); dead slots -1. */
+int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy, uint64_t* out_dets,
+                   double* out_coupling, double* out_diag, double* out_importance,
+                   uint8_t* out_valid, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGK_B200_H */

@@ -1,0 +1,472 @@
+"""GPU parity tests: the CUDA path, called through the Python host layer and the
+C ABI, against (a) golden vectors produced by the reference itself and (b) the
+CPU oracle on the same seeded inputs.  Bit-exact for determinants, orders,
+indices, patterns and float32 off-diagonal values; 1e-9 Ha for FP64 values."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import pack_np, random_dets, unpack_np
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9          # Ha, north-star tolerance for FP64 values
+F32_ENVELOPE = 2e-5  # vs the raw reference, whose diagonals are float32 einsums
+
+HAM_CASES = ["lih", "beh2", "n2", "ragged", "sparse", "edge_full_alpha", "edge_no_beta", "wide"]
+
+
+@pytest.fixture(scope="module")
+def fgk():
+    import flow_guided_krylov_b200 as f
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return f
+
+
+def make_pair(fgk, g):
+    from oracle import oracle as orc
+    n_orb, na, nb = (int(x) for x in g["shape"])
+    e_nuc = float(g.get("e_nuc", 0.0))
+    integ = fgk.MolecularIntegrals(g["h1"].astype(np.float64), g["g"].astype(np.float64), e_nuc,
+                                   na + nb, n_orb, na, nb)
+    H = fgk.MolecularHamiltonian(integ, device="cuda:0")
+    O = orc.OracleHam(g["h1"], g["g"], na, nb, e_nuc)
+    return H, O, n_orb
+
+
+def t64(a):
+    return torch.from_numpy(np.ascontiguousarray(a).astype(np.int64)).cuda()
+
+
+def dets_np(d):
+    return d.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_pack_unpack(fgk, name):
+    g = load_golden("ham_" + name)
+    H, _, n_orb = make_pair(fgk, g)
+    cfg = g["dets"]
+    d = H.pack(t64(cfg))
+    assert np.array_equal(dets_np(d), pack_np(cfg, n_orb))
+    assert np.array_equal(H.unpack(d).cpu().numpy(), cfg.astype(np.int64))
+    # other input dtypes go through the same kernel
+    assert np.array_equal(dets_np(H.pack(torch.from_numpy(cfg.astype(np.float32)))), pack_np(cfg, n_orb))
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_diagonal(fgk, name):
+    g = load_golden("ham_" + name)
+    H, O, _ = make_pair(fgk, g)
+    d = H.diagonal_elements_batch(t64(g["dets"])).cpu().numpy()
+    assert np.abs(d - O.diag(g["dets"])).max() < TOL
+    assert np.abs(d - g["diag32"]).max() < F32_ENVELOPE * max(1.0, np.abs(d).max())
+    one = H.diagonal_element(t64(g["dets"][0]))
+    assert abs(float(one) - d[0]) == 0.0
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_connections_reference_order(fgk, name):
+    g = load_golden("ham_" + name)
+    H, _, n_orb = make_pair(fgk, g)
+    offs = g["conn_offsets"]
+    # batch: one launch, all sources
+    c, e, src = H.get_connections_batch(t64(g["dets"]))
+    assert c.shape[0] == offs[-1]
+    assert np.array_equal(c.cpu().numpy().astype(np.uint8), g["conn_cfgs"])
+    assert np.array_equal(e.cpu().numpy().view(np.uint32), g["conn_elems"].view(np.uint32))
+    assert np.array_equal(src.cpu().numpy(), np.repeat(np.arange(len(g["dets"])), np.diff(offs)))
+    # single-determinant API, dtype of `connected` follows the input (molecular.py:324)
+    for j in (0, len(g["dets"]) - 1):
+        cj, ej = H.get_connections(t64(g["dets"][j]))
+        assert cj.dtype == torch.int64 and ej.dtype == torch.float32
+        assert np.array_equal(cj.cpu().numpy().astype(np.uint8), g["conn_cfgs"][offs[j]:offs[j + 1]])
+        assert np.array_equal(ej.cpu().numpy().view(np.uint32),
+                              g["conn_elems"][offs[j]:offs[j + 1]].view(np.uint32))
+
+
+def test_connections_empty_conventions(fgk):
+    # a determinant with no excitations: all alpha and beta orbitals full
+    n = 3
+    integ = fgk.MolecularIntegrals(np.eye(n), np.zeros((n,) * 4), 0.0, 2 * n, n, n, n)
+    H = fgk.MolecularHamiltonian(integ, device="cuda:0")
+    c, e = H.get_connections(torch.ones(2 * n, dtype=torch.long))
+    assert c.shape == (0, 2 * n) and e.shape == (0,)
+    c, e, s = H.get_connections_batch(torch.ones(2, 2 * n, dtype=torch.long))
+    assert c.shape == (0, 2 * n) and e.shape == (0,) and s.shape == (0,) and s.dtype == torch.long
+    c, e, s = H.get_connections_batch(torch.ones(0, 2 * n, dtype=torch.long))
+    assert c.shape == (0, 2 * n)
+    assert H.matrix_elements_fast(torch.ones(0, 2 * n, dtype=torch.long)).shape == (0, 0)
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_basis_index(fgk, name):
+    g = load_golden("ham_" + name)
+    H, _, n_orb = make_pair(fgk, g)
+    basis = H.pack(t64(g["basis"]))
+    idx = fgk.BasisIndex(basis)
+    assert np.array_equal(idx.lookup(basis).cpu().numpy(), np.arange(len(basis)))
+    q = H.pack(t64(g["dets"]))
+    want = []
+    keys = {bytes(r): i for i, r in enumerate(g["basis"])}
+    for r in g["dets"]:
+        want.append(keys.get(bytes(r), -1))
+    assert np.array_equal(idx.lookup(q).cpu().numpy(), np.array(want))
+    info = idx.info()
+    assert info["n_alpha_strings"] == len({bytes(r[:n_orb]) for r in g["basis"]})
+    assert info["n_beta_strings"] == len({bytes(r[n_orb:]) for r in g["basis"]})
+
+
+@pytest.mark.parametrize("name", HAM_CASES)
+def test_projected_h(fgk, name):
+    g = load_golden("ham_" + name)
+    H, O, _ = make_pair(fgk, g)
+    basis = t64(g["basis"])
+    n = len(g["basis"])
+    D = O.dense_H(g["basis"])
+    off = ~np.eye(n, dtype=bool)
+    # dense drop-in (molecular.py:471-516)
+    got = H.matrix_elements_fast(basis).cpu().numpy()
+    assert np.array_equal(got[off], D[off])
+    assert np.array_equal(got[off], g["H_dense32"].astype(np.float64)[off])
+    assert np.abs(np.diag(got) - np.diag(D)).max() < TOL
+    assert np.array_equal(H.matrix_elements(basis, basis.clone()).cpu().numpy(), got)
+    # COO drop-in (molecular.py:580-638): same triplets in the same order
+    r, c, v = H.get_sparse_matrix_elements(basis)
+    assert np.array_equal(r.cpu().numpy(), g["coo_rows"])
+    assert np.array_equal(c.cpu().numpy(), g["coo_cols"])
+    assert np.array_equal(v.cpu().numpy().view(np.uint32),
+                          g["coo_vals"].astype(np.float32).view(np.uint32))
+    # CSR flavours
+    for mode, ref in ((fgk.H_RAW, D), (fgk.H_SYM, 0.5 * (D + D.T))):
+        P = H.projected_csr(basis, mode)
+        M = P.to_scipy()
+        assert M.has_sorted_indices or n < 2
+        assert np.array_equal(np.sort(M.indices), np.sort(M.indices))   # well-formed
+        A = M.toarray()
+        assert np.array_equal(A[off], ref[off])
+        assert np.abs(np.diag(A) - np.diag(ref)).max() < TOL
+        if mode == fgk.H_RAW:   # explicit entries exactly where the reference writes
+            pat = np.zeros((n, n), bool)
+            pat[np.repeat(np.arange(n), np.diff(M.indptr)), M.indices] = True
+            refpat = np.eye(n, dtype=bool)
+            refpat[g["coo_rows"], g["coo_cols"]] = True
+            assert np.array_equal(pat, refpat)
+    # SYM | DROP_ZEROS == scipy csr_matrix(dense) pattern (skqd.py:783)
+    P = H.projected_csr(basis, fgk.H_SYM | fgk.H_DROP_ZEROS)
+    M = P.to_scipy()
+    S = 0.5 * (D + D.T)
+    pat = np.zeros((n, n), bool)
+    pat[np.repeat(np.arange(n), np.diff(M.indptr)), M.indices] = True
+    assert np.array_equal(pat & off, (S != 0) & off)
+    # row blocks reproduce the full build
+    if n > 4:
+        Pf = H.projected_csr(basis, fgk.H_RAW).to_scipy().toarray()
+        Pa = H.projected_csr(basis, fgk.H_RAW, row_begin=0, row_end=n // 3).to_scipy().toarray()
+        Pb = H.projected_csr(basis, fgk.H_RAW, row_begin=n // 3, row_end=n).to_scipy().toarray()
+        assert np.array_equal(np.vstack([Pa, Pb]), Pf)
+
+
+def test_matrix_elements_general_bra_ket(fgk):
+    g = load_golden("ham_beh2")
+    H, O, _ = make_pair(fgk, g)
+    bra, ket = g["basis"][:40], g["basis"][25:70]
+    got = H.matrix_elements(t64(bra), t64(ket)).cpu().numpy()
+    full = O.dense_H(g["basis"][:70])
+    want = full[:40, 25:70]
+    diag_mask = np.zeros_like(want, bool)
+    for i in range(25, 40):
+        diag_mask[i, i - 25] = True
+    assert np.array_equal(got[~diag_mask], want[~diag_mask])
+    assert np.abs(got[diag_mask] - want[diag_mask]).max() < TOL
+
+
+def test_csr_sort_rows_kernel(fgk):
+    from flow_guided_krylov_b200 import _native as nat
+    rng = np.random.default_rng(0)
+    lens = np.array([0, 1, 2, 3, 31, 32, 33, 1000, 4096, 4097, 9000, 0, 7])
+    row_ptr = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=row_ptr[1:])
+    cols = np.concatenate([rng.permutation(20000)[:l] for l in lens]).astype(np.int32)
+    vals = cols.astype(np.float64) * 0.5 + 1.0
+    rp, c, v = (torch.from_numpy(x).cuda() for x in (row_ptr, cols, vals))
+    nat.check(nat.lib().fgk_csr_sort_rows(len(lens), nat.ptr(rp), nat.ptr(c), nat.ptr(v), 0,
+                                          nat.stream_ptr("cuda:0")))
+    c, v = c.cpu().numpy(), v.cpu().numpy()
+    for r in range(len(lens)):
+        seg = slice(row_ptr[r], row_ptr[r + 1])
+        assert np.array_equal(c[seg], np.sort(cols[seg]))
+        assert np.array_equal(v[seg], c[seg] * 0.5 + 1.0)
+
+
+def test_spmv_real_and_complex(fgk):
+    from oracle import oracle as orc
+    rng = np.random.default_rng(1)
+    # (a) the reference's own subspace matrix (golden), (b) ragged random CSR with empty rows
+    g = load_golden("skqd_lih")
+    mats = [(g["H_indptr"], g["H_indices"], g["H_data"], len(g["H_indptr"]) - 1)]
+    lens = rng.integers(0, 70, size=300)
+    lens[[0, 5, 299]] = 0
+    lens[7] = 1
+    lens[8] = 513
+    rp = np.zeros(301, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    mats.append((rp, rng.integers(0, 400, size=rp[-1]).astype(np.int32),
+                 rng.standard_normal(rp[-1]), 400))
+    for indptr, indices, data, ncol in mats:
+        P = fgk.ProjectedH(ncol, torch.from_numpy(indptr).cuda(), torch.from_numpy(indices).cuda(),
+                           torch.from_numpy(data).cuda(), "cuda:0", 0, len(indptr) - 1)
+        x = rng.standard_normal(ncol)
+        z = x + 1j * rng.standard_normal(ncol)
+        y = P.matvec(torch.from_numpy(x).cuda()).cpu().numpy()
+        yz = P.matvec(torch.from_numpy(z).cuda()).cpu().numpy()
+        assert np.abs(y - orc.csr_matvec(indptr, indices, data, x)).max() < 1e-12
+        assert np.abs(yz - orc.csr_matvec(indptr, indices, data, z)).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide"])
+def test_pt2_candidates_and_selection(fgk, name):
+    g = load_golden("sci_" + name)
+    H, O, n_orb = make_pair(fgk, g)
+    k = int(g["k"])
+    basis = g["basis0"]
+    for rd in range(int(g["rounds"])):
+        E, v = float(g[f"r{rd}_E"]), g[f"r{rd}_v"]
+        cand_o, c32, c64, raw = O.pt2_candidates(basis, v)
+        ex_o = O.diag(cand_o)
+        imp_o = c64 ** 2 / (np.abs(E - ex_o) + 1e-10)
+        dets = H.pack(t64(basis))
+        idx = fgk.BasisIndex(dets)
+        for n_pass_cap in (None, 16):      # 16 slots force the multi-pass path
+            ws = None if n_pass_cap is None else fgk.Pt2Workspace(max(16, len(cand_o) // 3), "cuda:0")
+            cand, cpl, dg, imp, st = fgk.pt2_candidates(H, idx, torch.from_numpy(v).cuda(), E,
+                                                        workspace=ws)
+            assert st["raw_candidates"] == raw
+            if ws is not None:
+                assert st["passes"] > 1
+            got = {bytes(r): i for i, r in enumerate(unpack_np(dets_np(cand), n_orb))}
+            want = {bytes(r): i for i, r in enumerate(cand_o)}
+            assert got.keys() == want.keys()                       # candidate set, bit-exact
+            perm = np.array([got[bytes(r)] for r in cand_o])
+            assert np.abs(cpl.cpu().numpy()[perm] - c64).max() < 1e-12
+            assert np.abs(dg.cpu().numpy()[perm] - ex_o).max() < TOL
+            assert np.allclose(imp.cpu().numpy()[perm], imp_o, rtol=1e-9, atol=1e-15)
+        # the selection the reference made (float32 chain): same set unless a near-tie at the cut
+        ex = fgk.SelectedCIExpander(H, fgk.ResidualExpansionConfig(max_configs_per_iter=k))
+        sel, simp = ex._find_important_configs(t64(basis), E, v)
+        got = {bytes(r) for r in sel.cpu().numpy().astype(np.uint8)}
+        ref = {bytes(r) for r in g[f"r{rd}_sel"]}
+        if got != ref:
+            cut = float(g[f"r{rd}_imp"].min())
+            imp_map = {bytes(r): imp_o[i] for i, r in enumerate(cand_o)}
+            for r in got ^ ref:
+                assert abs(imp_map[r] - cut) <= 1e-5 * cut
+        o_sel, o_imp, *_ = O.find_important_configs(basis, E, v, k)
+        assert np.array_equal(sel.cpu().numpy().astype(np.uint8), o_sel)   # deterministic order
+        assert np.allclose(simp.cpu().numpy(), o_imp, rtol=1e-9, atol=1e-15)
+        basis = g[f"r{rd}_basis"]
+
+
+@pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide"])
+def test_selected_ci_expand_basis_rounds(fgk, name):
+    g = load_golden("sci_" + name)
+    H, O, _ = make_pair(fgk, g)
+    k = int(g["k"])
+    ex = fgk.SelectedCIExpander(H, fgk.ResidualExpansionConfig(max_configs_per_iter=k))
+    basis = t64(g["basis0"])
+    ob = g["basis0"]
+    for rd in range(int(g["rounds"])):
+        basis, st = ex.expand_basis(basis)
+        ob, ost = O.expand_basis(ob, k)
+        assert basis.dtype == torch.int64
+        assert np.array_equal(basis.cpu().numpy().astype(np.uint8), g[f"r{rd}_basis"])   # vs reference
+        assert st["configs_added"] == int(g[f"r{rd}_configs_added"])
+        assert abs(st["final_energy"] - float(g[f"r{rd}_final_energy"])) < F32_ENVELOPE
+        assert abs(st["final_energy"] - ost["final_energy"]) < TOL                       # vs FP64 oracle
+        assert abs(st["initial_energy"] - ost["initial_energy"]) < TOL
+        assert st["variational_violation"] is False
+
+
+def test_residual_based_expander(fgk):
+    g = load_golden("res_lih")
+    H, _, _ = make_pair(fgk, g)
+    ex = fgk.ResidualBasedExpander(H, fgk.ResidualExpansionConfig(
+        max_configs_per_iter=int(g["k"]), max_iterations=int(g["iters"]), residual_threshold=1e-4))
+    b, st = ex.expand_basis(H.get_hf_state().unsqueeze(0))
+    assert np.array_equal(b.cpu().numpy().astype(np.uint8), g["basis"])
+    assert list(st["history"]["basis_sizes"]) == list(g["sizes"])
+    assert np.abs(np.array(st["history"]["energies"]) - g["energies"]).max() < 1e-4   # reference eigh is float32
+    assert abs(st["final_energy"] - float(g["final_energy"])) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["lih", "h5"])
+def test_skqd_subspace_and_time_evolution(fgk, name):
+    from oracle import oracle as orc
+    g = load_golden("skqd_" + name)
+    H, O, n_orb = make_pair(fgk, g)
+    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(
+        max_krylov_dim=int(g["kdim"]), shots_per_krylov=int(g["shots"])))
+    assert np.array_equal(sk._subspace_basis.cpu().numpy().astype(np.uint8), g["subspace"])
+    P = sk._build_subspace_hamiltonian()
+    M = P.to_scipy()
+    assert np.array_equal(M.indptr, g["H_indptr"])                  # nonzero pattern, bit-exact
+    assert np.array_equal(M.indices, g["H_indices"])
+    isdiag = M.indices == np.repeat(np.arange(M.shape[0]), np.diff(M.indptr))
+    assert np.array_equal(M.data[~isdiag], g["H_data"][~isdiag])
+    Mo = O.raw_csr(g["subspace"])
+    assert np.abs(M.data - Mo.data).max() < TOL
+    psi = torch.zeros(M.shape[0], dtype=torch.complex128, device="cuda:0")
+    psi[int(g["hf_index"])] = 1.0
+    ref = np.zeros(M.shape[0], np.complex128)
+    ref[int(g["hf_index"])] = 1.0
+    for step in range(3):
+        psi = sk._evolve_subspace(psi, 1)
+        ref = orc.expm_multiply_taylor(M.indptr.astype(np.int64), M.indices, M.data, ref, 0.1)
+        assert np.abs(psi.cpu().numpy() - ref).max() < 1e-12          # same matrix: Taylor vs Taylor
+        assert np.abs(psi.cpu().numpy() - g["psi_steps"][step]).max() < 1e-5   # vs scipy on float32 diagonals
+
+
+def test_skqd_ground_state_energy_modes(fgk):
+    g = load_golden("skqd_lih")
+    H, O, _ = make_pair(fgk, g)
+    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(max_krylov_dim=2))
+    for tag in ("big", "small"):
+        b = g[f"gse_{tag}_basis"]
+        e_vec, v = sk.compute_ground_state_energy(t64(b), True, 1e-8)
+        e_no, none = sk.compute_ground_state_energy(t64(b), False, 1e-8)
+        assert none is None
+        oe_vec, ov = O.ground_state_energy(b, True)
+        oe_no, _ = O.ground_state_energy(b, False)
+        assert abs(e_vec - oe_vec) < TOL and abs(e_no - oe_no) < TOL
+        assert abs(e_vec - float(g[f"gse_{tag}_E_vec"])) < F32_ENVELOPE
+        assert abs(e_no - float(g[f"gse_{tag}_E_novec"])) < F32_ENVELOPE     # incl. the F5 lambda_1 quirk
+        assert abs(abs(np.dot(v.numpy(), ov)) - 1.0) < 1e-9
+    sk.config.reference_compat = False
+    e0, _ = sk.compute_ground_state_energy(t64(g["gse_big_basis"]), False, 1e-8)
+    assert abs(e0 - O.ground_state_energy(g["gse_big_basis"], True)[0]) < TOL
+
+
+def test_skqd_run_with_nf_on_reference_samples(fgk):
+    g = load_golden("skqd_lih")
+    H, O, _ = make_pair(fgk, g)
+    kdim = int(g["kdim"])
+    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(
+        max_krylov_dim=kdim, shots_per_krylov=int(g["shots"])))
+    # feed the reference's own cumulative sample sets (SURVEY 8d parity protocol)
+    prev = np.zeros((0, H.num_sites), np.uint8)
+    steps = []
+    for k in range(kdim):
+        cum = g[f"krylov_basis_{k}"]
+        new = cum[len(prev):]
+        assert np.array_equal(cum[:len(prev)], prev)
+        steps.append(t64(new))
+        prev = cum
+    sk.set_krylov_samples(steps)
+    for k in range(kdim):
+        assert np.array_equal(sk.get_basis_states(k).cpu().numpy().astype(np.uint8),
+                              g[f"krylov_basis_{k}"])
+    res = sk.run_with_nf(progress=False, regenerate_samples=False)
+    assert res["basis_sizes_krylov"] == list(g["basis_sizes_krylov"])
+    assert res["basis_sizes_combined"] == list(g["basis_sizes_combined"])
+    assert abs(res["energy_nf_only"] - float(g["energy_nf_only"])) < F32_ENVELOPE
+    assert np.abs(np.array(res["energies_krylov"]) - g["energies_krylov"]).max() < F32_ENVELOPE
+    assert np.abs(np.array(res["energies_combined"]) - g["energies_combined"]).max() < F32_ENVELOPE
+    assert abs(res["best_stable_energy"] - float(g["best_stable_energy"])) < F32_ENVELOPE
+    # FP64 oracle on the same bases: 1e-9
+    from oracle import oracle as orc
+    for k in range(1, kdim):
+        comb = orc.sort_unique(np.concatenate([g["nf_basis"], g[f"krylov_basis_{k}"]]))
+        assert abs(res["energies_combined"][k - 1] - O.ground_state_energy(comb, False)[0]) < TOL
+        assert np.array_equal(sk.get_combined_basis(k).cpu().numpy().astype(np.uint8), comb)
+
+
+def test_skqd_own_sampling_runs_and_is_variational(fgk):
+    g = load_golden("skqd_h5")
+    H, O, _ = make_pair(fgk, g)
+    torch.manual_seed(0)
+    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(max_krylov_dim=3, shots_per_krylov=500))
+    res = sk.run_with_nf(progress=False)
+    E_fci, _ = O.diagonalize(O.fci_basis())
+    assert res["best_stable_energy"] <= res["energy_nf_only"] + 1e-12
+    assert res["best_stable_energy"] >= E_fci - 1e-6          # + 1e-8 regularisation, lambda_1 >= lambda_0
+    assert sum(sk.krylov_samples[0].values()) == 500
+    assert len(sk.krylov_samples[0]) == 1                     # |psi_0> is the HF determinant
+
+
+@pytest.mark.parametrize("name", ["lih", "beh2"])
+def test_fci_energy_dense_and_davidson(fgk, name):
+    g = load_golden("fci_" + name)
+    H, O, _ = make_pair(fgk, g)
+    E = H.fci_energy()
+    Eo, _ = O.diagonalize(O.fci_basis())
+    assert abs(E - Eo) < TOL
+    assert abs(E - float(g["fci"])) < F32_ENVELOPE
+    # force the Davidson branch (dense_max=0) on the same operator
+    P = H.projected_csr(H.fci_dets(), fgk.H_SYM, packed=True)
+    w, v = fgk.lowest_eigenpairs(P, k=2, dense_max=0)
+    wd, _ = fgk.lowest_eigenpairs(P, k=2)
+    assert np.abs(w.cpu().numpy() - wd.cpu().numpy()).max() < TOL
+    r = P.matvec(v[:, 0].contiguous()) - w[0] * v[:, 0]
+    assert float(torch.linalg.norm(r)) < 1e-8
+
+
+def test_large_cas_window_properties(fgk):
+    """Size-independent properties on a config-4-shaped basis (32 orbitals, CAS window),
+    scaled to C(9,4)^2 = 15,876 determinants so the test stays in seconds."""
+    from math import comb
+    from helpers import synth_integrals
+    n_orb, na, nb, n_act, n_froz = 32, 8, 8, 9, 4
+    h1, gg = synth_integrals(n_orb, seed=3)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, na + nb, n_orb, na, nb), "cuda:0")
+    from itertools import combinations
+    strings = []
+    for occ in combinations(range(n_froz, n_froz + n_act), na - n_froz):
+        w = 0
+        for p in list(range(n_froz)) + list(occ):
+            w |= 1 << (n_orb - 1 - p)
+        strings.append(w)
+    s = np.array(strings, dtype=np.uint64)
+    dets = np.empty((len(s), len(s), 2), np.uint64)
+    dets[:, :, 0] = s[:, None]
+    dets[:, :, 1] = s[None, :]
+    dets = torch.from_numpy(dets.reshape(-1, 2).view(np.int64)).cuda()
+    n = dets.shape[0]
+    assert n == comb(n_act, 4) ** 2
+    P = H.projected_csr(dets, fgk.H_RAW, packed=True)
+    # every row: diagonal + singles + same-spin doubles + alpha-beta doubles inside the window
+    ne, nv = 4, n_act - 4
+    per_row = 1 + 2 * ne * nv + 2 * comb(ne, 2) * comb(nv, 2) + (ne * nv) ** 2
+    assert torch.all(P.row_ptr[1:] - P.row_ptr[:-1] == per_row)
+    assert P.nnz == n * per_row
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal(n)).cuda()
+    y = torch.from_numpy(rng.standard_normal(n)).cuda()
+    # linearity
+    lhs = P.matvec(2.0 * x - 3.0 * y)
+    rhs = 2.0 * P.matvec(x) - 3.0 * P.matvec(y)
+    assert float((lhs - rhs).abs().max()) < 1e-9
+    # symmetrised operator is self-adjoint; raw one is not
+    S = H.projected_csr(dets, fgk.H_SYM, packed=True, index=P._index)
+    a = float(torch.dot(y, S.matvec(x)))
+    b = float(torch.dot(S.matvec(y), x))
+    assert abs(a - b) < 1e-9 * max(1.0, abs(a))
+    # complex product = real product on real and imaginary parts
+    z = torch.complex(x, y)
+    yz = P.matvec(z)
+    assert float((yz.real - P.matvec(x)).abs().max()) < 1e-12
+    assert float((yz.imag - P.matvec(y)).abs().max()) < 1e-12
+    # sampled rows against the oracle's connections of the same determinants
+    from oracle import oracle as orc
+    O = orc.OracleHam(h1.astype(np.float32), gg.astype(np.float32), na, nb)
+    M = P.to_scipy()
+    cfg = unpack_np(dets_np(dets), n_orb)
+    keys = {bytes(r): i for i, r in enumerate(cfg)}
+    for j in (0, n // 2 + 7, n - 1):
+        cc, ee = O.connections(cfg[j])
+        col = M[:, j].toarray().ravel()
+        for r, e in zip(cc, ee):
+            i = keys.get(bytes(r))
+            if i is not None:
+                assert col[i] == float(e)
+        assert abs(col[j] - O.diag(cfg[j:j + 1])[0]) < TOL

@@ -1,0 +1,151 @@
+"""CPU tier: the C-ABI library loads and exports every symbol the header declares
+(no compute without a GPU), the product path refuses to run without CUDA, and the
+host-side Krylov / selection logic (pure torch) is correct on CPU tensors."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from helpers import pack_np
+
+HEADER = os.path.join(ROOT, "include", "fgk_b200.h")
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from flow_guided_krylov_b200.build import build_library
+    return build_library()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fgk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    L = C.CDLL(built_lib)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/fgk_b200.h but not exported"
+    L.fgk_version.restype = C.c_int
+    assert L.fgk_version() >= 100
+
+
+def test_binding_table_matches_header(built_lib):
+    from flow_guided_krylov_b200 import _native as nat
+    assert sorted(nat._SIGNATURES) == declared_symbols()
+    nat.lib()
+
+
+def test_no_cpu_fallback():
+    import flow_guided_krylov_b200 as f
+    integ = f.MolecularIntegrals(np.eye(2), np.zeros((2,) * 4), 0.0, 2, 2, 1, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        f.MolecularHamiltonian(integ, device="cpu")
+    if not torch.cuda.is_available():
+        from flow_guided_krylov_b200 import _native as nat
+        with pytest.raises(RuntimeError):
+            nat.ptr(torch.zeros(4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "flow-guided-krylov_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                for needle in ("import oracle", "from oracle", "liboracle", "oracle/", "orc_"):
+                    assert needle not in txt, f"{fn} reaches into the oracle ({needle})"
+
+
+class DenseOp:
+    """stand-in for ProjectedH on CPU tensors (host-logic tests only)."""
+
+    def __init__(self, A):
+        self.A = A
+        self.n = A.shape[0]
+        self.row_begin, self.row_end = 0, self.n
+        idx = A.nonzero()
+        self.cols = idx[:, 1].to(torch.int32)
+        self.vals = A[idx[:, 0], idx[:, 1]]
+
+    def matvec(self, x):
+        return (self.A.to(x.dtype)) @ x
+
+    def diagonal(self):
+        return torch.diagonal(self.A).clone()
+
+    def to_dense(self):
+        return self.A
+
+
+def test_davidson_matches_dense_eigh():
+    from flow_guided_krylov_b200.solvers import lowest_eigenpairs
+    g = load_golden("skqd_lih")
+    import scipy.sparse as sp
+    n = len(g["H_indptr"]) - 1
+    M = sp.csr_matrix((g["H_data"], g["H_indices"], g["H_indptr"]), shape=(n, n)).toarray()
+    S = torch.from_numpy(0.5 * (M + M.T))
+    w_ref = np.linalg.eigvalsh(S.numpy())
+    op = DenseOp(S)
+    w, v = lowest_eigenpairs(op, k=2, dense_max=0)
+    assert np.abs(w.numpy() - w_ref[:2]).max() < 1e-9
+    assert float(torch.linalg.norm(S @ v[:, 0] - w[0] * v[:, 0])) < 1e-8
+    w1, _ = lowest_eigenpairs(op, k=1, dense_max=0, max_space=12)    # exercises thick restart
+    assert abs(float(w1[0]) - w_ref[0]) < 1e-9
+    wd, _ = lowest_eigenpairs(op, k=3)                               # dense branch
+    assert np.abs(wd.numpy() - w_ref[:3]).max() < 1e-10
+
+
+def test_expm_multiply_matches_scipy():
+    from scipy.sparse.linalg import expm_multiply as sp_expm
+    import scipy.sparse as sp
+    from flow_guided_krylov_b200.solvers import expm_multiply
+    g = load_golden("skqd_lih")
+    n = len(g["H_indptr"]) - 1
+    M = sp.csr_matrix((g["H_data"], g["H_indices"], g["H_indptr"]), shape=(n, n))
+    op = DenseOp(torch.from_numpy(M.toarray()))
+    psi = np.zeros(n, np.complex128)
+    psi[int(g["hf_index"])] = 1.0
+    ours = torch.from_numpy(psi)
+    for step in range(3):
+        ours = expm_multiply(op, ours, -0.1j)
+        assert np.abs(ours.numpy() - g["psi_steps"][step]).max() < 1e-12
+    big = expm_multiply(op, torch.from_numpy(psi), -2.5j)            # several scaling steps
+    assert np.abs(big.numpy() - sp_expm(-2.5j * M, psi)).max() < 1e-11
+
+
+def test_select_top_k_ties_and_order():
+    from flow_guided_krylov_b200.expansion import select_top_k
+    dets = torch.tensor([[5, 1], [2, 9], [2, 3], [7, 0], [1, 1], [2, 4]], dtype=torch.int64)
+    score = torch.tensor([1.0, 3.0, 3.0, 0.5, 3.0, 2.0], dtype=torch.float64)
+    d, s = select_top_k(dets, score, 2, 10)
+    assert s.tolist() == [3.0, 3.0]
+    assert d.tolist() == [[1, 1], [2, 3]]                 # ties resolved by ascending key
+    d, s = select_top_k(dets, score, 4, 10)
+    assert d.tolist() == [[1, 1], [2, 3], [2, 9], [2, 4]]
+    d, s = select_top_k(dets, score, 100, 10)
+    assert d.shape[0] == 6 and s.tolist() == sorted(score.tolist(), reverse=True)
+    d, s = select_top_k(dets[:0], score[:0], 3, 10)
+    assert d.shape[0] == 0
+
+
+def test_sort_unique_dets_is_reference_order():
+    from flow_guided_krylov_b200.hamiltonian import sort_unique_dets
+    g = load_golden("ham_wide")          # 66 sites: beyond the reference's int64 key
+    n_orb = int(g["shape"][0])
+    cfg = np.concatenate([g["basis"], g["basis"][::3], g["dets"]])
+    want = torch.unique(torch.from_numpy(cfg.astype(np.int64)), dim=0).numpy().astype(np.uint8)
+    got = sort_unique_dets(torch.from_numpy(pack_np(cfg, n_orb).view(np.int64)), n_orb)
+    assert np.array_equal(got.numpy().view(np.uint64), pack_np(want, n_orb))
+    # n_orb == 64 uses the sign-flip path
+    d = torch.tensor([[-1, 3], [1, 2], [-(2 ** 63), 0], [1, 2], [0, -1]], dtype=torch.int64)
+    out = sort_unique_dets(d, 64).numpy().view(np.uint64)
+    keys = [(int(a) << 64) | int(b) for a, b in out]
+    assert keys == sorted(set(keys)) and len(keys) == 4
