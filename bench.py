@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the determinant-space Hamiltonian engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], the one the north-star target is quoted on):
+synthetic random-integral Hamiltonian, 32 orbitals / 8+8 electrons, CAS(8e,14o)
+window basis of C(14,4)^2 = 1,002,001 determinants, projected H in
+FP64 CSR (2,221 nnz/row, 2.2255e9 nnz, 26.7 GB).
+
+One STEP = one sparse H.v over the whole basis (the product behind every Krylov /
+Davidson / expm iteration of Stage 4).  `value` = H nonzeros processed per second,
+inputs resident in HBM; `e2e` = the same through the public host-buffer API
+(x from pinned host memory, y back to the host, every step).  The projected-H
+build (H nonzeros produced/s) and a PT2 expansion sweep (candidates/s) are timed in
+the same run and reported in the "build" and "pt2" objects.  With N > 1 the rows are
+sharded over the ranks (strong scaling) and a step also all-gathers the result
+vector over NCCL, as a Krylov iteration must.
+
+--impl reference times the CPU restatement of the reference (oracle/, a C port --
+the reference is pure Python and cannot travel to the GPU box) on the host cores,
+on a bounded sample of the same workload, and prints the same JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from itertools import combinations
+from math import comb
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "H nonzeros/s (FP64 CSR H.v over the 32-orbital 1,002,001-determinant basis)"
+UNIT = "nnz/s"
+
+
+# ---- workload ----------------------------------------------------------------------------
+def synth_integrals(n_orb, seed=0, h1_scale=1.0, h2_scale=0.1):
+    """SURVEY Appendix D generator + the molecule-like shift it recommends (HF-like gap)."""
+    rng = np.random.default_rng(seed)
+    h1 = rng.standard_normal((n_orb, n_orb)) * h1_scale
+    h1 = 0.5 * (h1 + h1.T)
+    g = rng.standard_normal((n_orb,) * 4) * h2_scale
+    g = g + g.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    h1 = h1 + np.diag(np.linspace(-2.0, 2.0, n_orb))
+    idx = np.arange(n_orb)
+    g[idx[:, None], idx[:, None], idx[None, :], idx[None, :]] += 0.3
+    return h1, g
+
+
+def cas_window_strings(n_orb, n_frozen, n_active, n_act_el):
+    out = []
+    for occ in combinations(range(n_frozen, n_frozen + n_active), n_act_el):
+        w = 0
+        for p in list(range(n_frozen)) + list(occ):
+            w |= 1 << (n_orb - 1 - p)
+        out.append(w)
+    return np.array(sorted(out), dtype=np.uint64)
+
+
+def cas_window_basis(n_orb, n_frozen, n_active, n_act_el):
+    """(n,2) uint64 packed determinants, ascending key (alpha-major)."""
+    s = cas_window_strings(n_orb, n_frozen, n_active, n_act_el)
+    d = np.empty((len(s), len(s), 2), np.uint64)
+    d[:, :, 0] = s[:, None]
+    d[:, :, 1] = s[None, :]
+    return d.reshape(-1, 2)
+
+
+def unpack_np(dets, n_orb):
+    sh = np.arange(n_orb - 1, -1, -1, dtype=np.uint64)
+    a = ((dets[:, 0:1] >> sh) & np.uint64(1)).astype(np.uint8)
+    b = ((dets[:, 1:2] >> sh) & np.uint64(1)).astype(np.uint8)
+    return np.concatenate([a, b], axis=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the SpMV kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "spmv_dram_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# ---- CPU arm (oracle port of the reference) -------------------------------------------------
+def cpu_sample_csr(args, n_rows_sample, seed=0, tile_to_nnz=0):
+    """Bounded sample of the workload built by the CPU oracle: the reference's own loop
+    (get_connections per ket + basis lookup, molecular.py:504-514 / skqd.py:390-410) over
+    `n_rows_sample` kets of the basis, one CSR row per ket (same nnz/row as the GPU rows).
+    tile_to_nnz > 0 repeats the sampled rows with rotated column ids until the matrix has
+    that many nonzeros, so that the CPU SpMV streams from DRAM like the real one would
+    instead of sitting in the CPU caches.
+    Returns (indptr, indices, data, n, build_s, cores, raw_connections, built_nnz)."""
+    from oracle import oracle as orc
+    h1, g = synth_integrals(args.n_orb, seed=0)
+    O = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), args.n_alpha, args.n_beta)
+    dets = cas_window_basis(args.n_orb, args.n_frozen, args.n_active, args.n_act_el)
+    n = len(dets)
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(n, size=min(n_rows_sample, n), replace=False)).astype(np.int64)
+    cfg_all = unpack_np(dets, args.n_orb)            # (n, 2*n_orb) bytes: 64 MB at 1e6
+    t0 = time.perf_counter()
+    rows, cols, vals = O.offdiag_coo_kets(cfg_all, pick)     # cols = position in `pick`
+    diag = O.diag(cfg_all[pick])
+    build_s = time.perf_counter() - t0
+    cnt = np.zeros(len(pick), np.int64)
+    O_lib = orc.lib()
+    O_lib.orc_connections_count(O._h, cfg_all[pick].ctypes.data, len(pick), cnt.ctypes.data)
+    raw = int(cnt.sum())
+    m = len(pick)
+    counts = np.bincount(cols, minlength=m) + 1
+    indptr = np.zeros(m + 1, np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    indices = np.empty(indptr[-1], np.int32)
+    data = np.empty(indptr[-1], np.float64)
+    indices[indptr[:-1]] = pick.astype(np.int32)
+    data[indptr[:-1]] = diag
+    within = np.arange(len(cols)) - np.searchsorted(cols, cols, side="left")   # cols is sorted
+    dst = indptr[cols] + 1 + within
+    indices[dst] = rows.astype(np.int32)
+    data[dst] = vals.astype(np.float64)
+    if tile_to_nnz and len(data) < tile_to_nnz:
+        reps = int(-(-tile_to_nnz // len(data)))
+        idx_t = np.concatenate([(indices.astype(np.int64) + t * 7919 * 127) % n for t in range(reps)]).astype(np.int32)
+        data_t = np.tile(data, reps)
+        ptr_t = np.concatenate([[0], np.cumsum(np.tile(counts, reps))]).astype(np.int64)
+        indptr, indices, data = ptr_t, idx_t, data_t
+    return indptr, indices, data, n, build_s, orc.lib().orc_num_threads(), raw, int(len(cols) + m)
+
+
+def cpu_spmv_rate(indptr, indices, data, n, min_seconds):
+    from oracle import oracle as orc
+    x = np.random.default_rng(1).standard_normal(n)
+    orc.csr_matvec(indptr, indices, data, x)                 # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        orc.csr_matvec(indptr, indices, data, x)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds and reps >= 3:
+            break
+    return len(data) * reps / el, reps, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    indptr, indices, data, n, build_s, cores, raw, built_nnz = cpu_sample_csr(
+        args, args.cpu_sample_rows, tile_to_nnz=int(args.cpu_step_nnz))
+    nnz = len(data)
+    x = np.random.default_rng(1).standard_normal(n)
+    from oracle import oracle as orc
+    for _ in range(args.warmup):
+        orc.csr_matvec(indptr, indices, data, x)
+    reps_per_step = 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(reps_per_step):
+            orc.csr_matvec(indptr, indices, data, x)
+    el = time.perf_counter() - t0
+    value = nnz * reps_per_step * args.steps / el
+    sample = (f"{args.cpu_sample_rows} kets of the basis ({built_nnz} nnz) built by the oracle port of "
+              f"get_connections+lookup, tiled with rotated columns to {nnz} nnz (DRAM-resident); "
+              f"one csr_matvec over it per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, "cpu sample"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build": {"value": built_nnz / build_s, "unit": "H nnz built/s", "raw_connections_per_s": raw / build_s,
+                  "seconds": build_s, "cores": cores},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, l2_note):
+    n = comb(args.n_active, args.n_act_el) ** 2
+    return {"workload": f"configs[3]: synthetic {args.n_orb}-orbital {args.n_alpha}+{args.n_beta}-electron "
+                        f"Hamiltonian, CAS({2 * args.n_act_el}e,{args.n_active}o) window basis, {n} determinants",
+            "n_orb": args.n_orb, "n_dets": n, "flavour": "0.5*(H+H^T) CSR, FP64 values, int32 columns",
+            "l2": l2_note}
+
+
+# ---- GPU arm -------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import flow_guided_krylov_b200 as fgk
+    from flow_guided_krylov_b200 import dist as fdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    h1, g = synth_integrals(args.n_orb, seed=0)
+    H = fgk.MolecularHamiltonian(
+        fgk.MolecularIntegrals(h1, g, 0.0, args.n_alpha + args.n_beta, args.n_orb, args.n_alpha, args.n_beta), dev)
+    dets_np = cas_window_basis(args.n_orb, args.n_frozen, args.n_active, args.n_act_el)
+    n = len(dets_np)
+    dets = torch.from_numpy(dets_np.view(np.int64)).to(dev)
+
+    # ---- projected-H build (timed on the device, reported beside the headline) ----
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    index = fgk.BasisIndex(dets)
+    ev[1].record()
+    lo, hi = fdist.row_block(n, rank, world)
+    P = H.projected_csr(dets, fgk.H_SYM, row_begin=lo, row_end=hi, index=index, packed=True,
+                        sort_rows=False)
+    ev[2].record()
+    if args.sort_rows:
+        P.sort_rows()
+    ev[3].record()
+    barrier()
+    t_index, t_build, t_sort = (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]),
+                                ev[2].elapsed_time(ev[3]))
+    nnz_local = P.nnz
+    tt = torch.tensor([nnz_local, t_index + t_build + t_sort], dtype=torch.float64, device=dev)
+    if world > 1:
+        nn = tt.clone()
+        dist.all_reduce(nn[:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(tt[1:], op=dist.ReduceOp.MAX)
+        tt[0] = nn[0]
+    nnz_total, build_ms = float(tt[0]), float(tt[1])
+    build = {"value": nnz_total / (build_ms * 1e-3), "unit": "H nnz built/s", "ms": build_ms,
+             "index_ms": t_index, "count_fill_ms": t_build, "sort_ms": t_sort, "nnz": nnz_total,
+             "launches": 6 + 2 + (1 if args.sort_rows else 0)}
+
+    # ---- headline: K sparse H.v ----------------------------------------------------
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    x_host = torch.randn(n, dtype=torch.float64, generator=gen).pin_memory()
+    x = x_host.to(dev)
+    per = -(-n // world)
+    y_local = torch.empty(P.n_rows, dtype=torch.float64, device=dev)
+
+    def step(xv):
+        P.matvec(xv, out=y_local)
+        if world > 1:
+            return fdist.allgather_vector(y_local, n)
+        return y_local
+
+    for _ in range(max(args.warmup, 3)):
+        step(x)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # dominant kernel alone (no collective), per launch
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        P.matvec(x, out=y_local)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+
+    # ---- e2e: host buffers through the public API -----------------------------------
+    y_host = torch.empty(P.n_rows, dtype=torch.float64).pin_memory()
+    xd = torch.empty(n, dtype=torch.float64, device=dev)
+
+    def e2e_step():
+        xd.copy_(x_host, non_blocking=True)             # H2D of this step's input
+        P.matvec(xd, out=y_local)
+        y_host.copy_(y_local, non_blocking=True)        # D2H of this step's result
+        torch.cuda.current_stream().synchronize()       # the caller owns y_host now
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    tmax = torch.tensor([ms, kern_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, kern_ms, e2e_s = (float(v) for v in tmax)
+
+    # ---- PT2 sweep (candidates/s), same Hamiltonian and basis -------------------------
+    pt2 = None
+    if args.pt2_sources > 0:
+        ns = min(args.pt2_sources, n)
+        coeff = torch.zeros(n, dtype=torch.float64, device=dev)
+        coeff[:ns] = torch.exp(-torch.arange(ns, dtype=torch.float64, device=dev) / (0.25 * ns))
+        coeff /= torch.linalg.norm(coeff)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500)
+        p1.record()
+        barrier()
+        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+        pt2 = {"value": st["raw_candidates_total"] / (float(pms[0]) * 1e-3), "unit": "PT2 candidates/s",
+               "raw_candidates": st["raw_candidates_total"], "sources": ns, "ms": float(pms[0]),
+               "passes": st["passes"], "selected": int(sel.shape[0])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        indptr, indices, data, _, b_s, cores, raw, built_nnz = cpu_sample_csr(
+            args, args.cpu_sample_rows, tile_to_nnz=int(args.cpu_step_nnz))
+        rate, reps, el = cpu_spmv_rate(indptr, indices, data, n, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample_rows} kets of the same basis ({built_nnz} nnz, oracle-built at "
+                         f"{built_nnz / b_s:.3g} H nnz/s = {raw / b_s:.3g} connections/s), tiled with rotated "
+                         f"columns to {len(data)} nnz; oracle csr_matvec x{reps} in {el:.1f}s",
+               "build_nnz_per_s": built_nnz / b_s, "connections_per_s": raw / b_s}
+
+    peak, which = measured_peak()
+    bytes_per_launch = 12.0 * nnz_local + 20.0 * P.n_rows
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    line = {
+        "metric": METRIC, "value": nnz_total * args.steps / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, "matrix (26.7 GB at full size) is larger than L2; no flush needed"),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
+                     "kernel": "k_spmv_csr_vector<false,4>", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": which,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "cpu_baseline": cpu,
+        "e2e": {"value": nnz_total * args.steps / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * P.n_rows,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "clocks": clocks,
+        "gpu_launches": args.steps,
+        "build": build, "pt2": pt2,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    # workload shape (defaults = BASELINE.json configs[3]); smaller --n-active for dry runs
+    ap.add_argument("--n-orb", type=int, default=32)
+    ap.add_argument("--n-alpha", type=int, default=8)
+    ap.add_argument("--n-beta", type=int, default=8)
+    ap.add_argument("--n-frozen", type=int, default=4)
+    ap.add_argument("--n-active", type=int, default=14)
+    ap.add_argument("--n-act-el", type=int, default=4)
+    ap.add_argument("--sort-rows", action="store_true", help="also sort CSR rows by column")
+    ap.add_argument("--pt2-sources", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--cpu-step-nnz", type=float, default=1e8,
+                    help="CPU arms: nonzeros of the (tiled) sample matrix = nnz per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,9 +44,13 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=400, max_space=None, matvec=No
     V = torch.zeros(n, nb, dtype=torch.float64, device=dev)
     start = torch.argsort(diag)[:nb]
     V[start, torch.arange(nb, device=dev)] = 1.0
+    # A seeded random admixture: unit vectors alone can be orthogonal to a whole
+    # symmetry sector (e.g. triplets), which residual norms cannot detect.
+    gen = torch.Generator(device="cpu").manual_seed(20240229)
+    V += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen).to(dev)
     if v0 is not None:
         V[:, 0] = v0.to(dev, torch.float64)
-        V, _ = torch.linalg.qr(V)
+    V, _ = torch.linalg.qr(V)
     W = torch.stack([mv(V[:, i].contiguous()) for i in range(V.shape[1])], dim=1)
     w = X = None
     for _ in range(max_iter):

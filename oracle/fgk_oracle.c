@@ -337,17 +337,37 @@ static long lookup(const uint8_t *cfgs, const long *perm, long n, int S, const u
  * (j ascending, emission order inside j).  Two-phase: pass rows==NULL to count.
  * Also the loop of matrix_elements_fast (:504-514) and of
  * _build_subspace_hamiltonian (skqd.py:390-410). */
+static long offdiag_coo_impl(const orc_ham *H, const uint8_t *cfgs, long n,
+                             const int64_t *kets, long n_kets, int64_t *rows,
+                             int64_t *cols, float *vals, long cap);
+
 long orc_offdiag_coo(const orc_ham *H, const uint8_t *cfgs, long n, int64_t *rows,
                      int64_t *cols, float *vals, long cap)
 {
+    return offdiag_coo_impl(H, cfgs, n, NULL, n, rows, cols, vals, cap);
+}
+
+/* same loop restricted to the kets listed in `kets` (a bounded sample of a large
+ * basis); cols[] then holds the POSITION in `kets`, rows[] the basis index */
+long orc_offdiag_coo_kets(const orc_ham *H, const uint8_t *cfgs, long n, const int64_t *kets,
+                          long n_kets, int64_t *rows, int64_t *cols, float *vals, long cap)
+{
+    return offdiag_coo_impl(H, cfgs, n, kets, n_kets, rows, cols, vals, cap);
+}
+
+static long offdiag_coo_impl(const orc_ham *H, const uint8_t *cfgs, long n,
+                             const int64_t *kets, long n_kets, int64_t *rows,
+                             int64_t *cols, float *vals, long cap)
+{
     int S = 2 * H->n_orb;
     long *perm = sorted_perm(cfgs, n, S);
-    long *cnt = (long *)calloc(n + 1, sizeof(long));
+    long *cnt = (long *)calloc(n_kets + 1, sizeof(long));
 #pragma omp parallel
     {
         long cap_c = 0; uint8_t *bc = NULL; float *be = NULL;
 #pragma omp for schedule(dynamic, 4)
-        for (long j = 0; j < n; j++) {
+        for (long jj = 0; jj < n_kets; jj++) {
+            long j = kets ? kets[jj] : jj;
             long m = orc_connections(H, cfgs + j * S, NULL, NULL, 0);
             if (m > cap_c) {
                 cap_c = m; free(bc); free(be);
@@ -357,28 +377,29 @@ long orc_offdiag_coo(const orc_ham *H, const uint8_t *cfgs, long n, int64_t *row
             long c = 0;
             for (long k = 0; k < m; k++)
                 if (lookup(cfgs, perm, n, S, bc + k * S) >= 0) c++;
-            cnt[j + 1] = c;
+            cnt[jj + 1] = c;
         }
         free(bc); free(be);
     }
-    for (long j = 0; j < n; j++) cnt[j + 1] += cnt[j];
-    long total = cnt[n];
+    for (long j = 0; j < n_kets; j++) cnt[j + 1] += cnt[j];
+    long total = cnt[n_kets];
     if (rows && total <= cap) {
 #pragma omp parallel
         {
             long cap_c = 0; uint8_t *bc = NULL; float *be = NULL;
 #pragma omp for schedule(dynamic, 4)
-            for (long j = 0; j < n; j++) {
+            for (long jj = 0; jj < n_kets; jj++) {
+                long j = kets ? kets[jj] : jj;
                 long m = orc_connections(H, cfgs + j * S, NULL, NULL, 0);
                 if (m > cap_c) {
                     cap_c = m; free(bc); free(be);
                     bc = (uint8_t *)malloc((size_t)m * S); be = (float *)malloc(sizeof(float) * m);
                 }
                 orc_connections(H, cfgs + j * S, bc, be, m);
-                long o = cnt[j];
+                long o = cnt[jj];
                 for (long k = 0; k < m; k++) {
                     long i = lookup(cfgs, perm, n, S, bc + k * S);
-                    if (i >= 0) { rows[o] = i; cols[o] = j; vals[o] = be[k]; o++; }
+                    if (i >= 0) { rows[o] = i; cols[o] = jj; vals[o] = be[k]; o++; }
                 }
             }
             free(bc); free(be);

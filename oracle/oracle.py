@@ -53,6 +53,8 @@ def lib():
         L.orc_connections_fill.argtypes = [vp, vp, i64, vp, vp, vp, vp]
         L.orc_offdiag_coo.restype = i64
         L.orc_offdiag_coo.argtypes = [vp, vp, i64, vp, vp, vp, i64]
+        L.orc_offdiag_coo_kets.restype = i64
+        L.orc_offdiag_coo_kets.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, i64]
         L.orc_pt2_candidates.restype = i64
         L.orc_pt2_candidates.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp]
         L.orc_csr_matvec_f64.argtypes = [i64, vp, vp, vp, vp, vp]
@@ -158,6 +160,18 @@ class OracleHam:
         c = np.empty(tot, np.int64)
         v = np.empty(tot, np.float32)
         lib().orc_offdiag_coo(self._h, _p(basis), n, _p(r), _p(c), _p(v), tot)
+        return r, c, v
+
+    def offdiag_coo_kets(self, basis, kets):
+        """the same loop for a subset of kets; cols = position in `kets`."""
+        basis = _u8(basis).reshape(-1, self.S)
+        kets = np.ascontiguousarray(kets, np.int64)
+        n = len(basis)
+        tot = lib().orc_offdiag_coo_kets(self._h, _p(basis), n, _p(kets), len(kets), None, None, None, 0)
+        r = np.empty(tot, np.int64)
+        c = np.empty(tot, np.int64)
+        v = np.empty(tot, np.float32)
+        lib().orc_offdiag_coo_kets(self._h, _p(basis), n, _p(kets), len(kets), _p(r), _p(c), _p(v), tot)
         return r, c, v
 
     # molecular.py:471-516 matrix_elements_fast (dense; FP64 diagonal, exact
