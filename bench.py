@@ -256,7 +256,7 @@ def workload_config(args, l2_note):
     n = comb(args.n_active, args.n_act_el) ** 2
     return {"workload": f"configs[3]: synthetic {args.n_orb}-orbital {args.n_alpha}+{args.n_beta}-electron "
                         f"Hamiltonian, CAS({2 * args.n_act_el}e,{args.n_active}o) window basis, {n} determinants",
-            "n_orb": args.n_orb, "n_dets": n, "flavour": "0.5*(H+H^T) CSR, FP64 values, int32 columns",
+            "n_orb": args.n_orb, "n_dets": n, "flavour": "0.5*(H+H^T), FP64 values, int32 columns, CSR + SELL-32 copy for H.v",
             "l2": l2_note}
 
 
@@ -290,7 +290,7 @@ def run_ours(args):
 
     # ---- projected-H build (timed on the device, reported beside the headline) ----
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
     index = fgk.BasisIndex(dets)
     ev[1].record()
@@ -298,14 +298,17 @@ def run_ours(args):
     P = H.projected_csr(dets, fgk.H_SYM, row_begin=lo, row_end=hi, index=index, packed=True,
                         sort_rows=False)
     ev[2].record()
-    if args.sort_rows:
+    if not args.no_sort_rows:
         P.sort_rows()
     ev[3].record()
+    if args.format == "sell":
+        P.to_sell()
+    ev[4].record()
     barrier()
-    t_index, t_build, t_sort = (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]),
-                                ev[2].elapsed_time(ev[3]))
+    t_index, t_build, t_sort, t_sell = (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]),
+                                        ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4]))
     nnz_local = P.nnz
-    tt = torch.tensor([nnz_local, t_index + t_build + t_sort], dtype=torch.float64, device=dev)
+    tt = torch.tensor([nnz_local, t_index + t_build + t_sort + t_sell], dtype=torch.float64, device=dev)
     if world > 1:
         nn = tt.clone()
         dist.all_reduce(nn[:1], op=dist.ReduceOp.SUM)
@@ -313,8 +316,8 @@ def run_ours(args):
         tt[0] = nn[0]
     nnz_total, build_ms = float(tt[0]), float(tt[1])
     build = {"value": nnz_total / (build_ms * 1e-3), "unit": "H nnz built/s", "ms": build_ms,
-             "index_ms": t_index, "count_fill_ms": t_build, "sort_ms": t_sort, "nnz": nnz_total,
-             "launches": 6 + 2 + (1 if args.sort_rows else 0)}
+             "index_ms": t_index, "count_fill_ms": t_build, "sort_ms": t_sort, "to_sell_ms": t_sell,
+             "nnz": nnz_total, "launches": 6 + 2 + (0 if args.no_sort_rows else 1) + (1 if args.format == "sell" else 0)}
 
     # ---- headline: K sparse H.v ----------------------------------------------------
     gen = torch.Generator(device="cpu").manual_seed(1)
@@ -350,6 +353,14 @@ def run_ours(args):
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / args.steps
+    alt_ms = None
+    if args.format == "sell":          # the plain CSR-vector kernel on the same operator, for reference
+        k0.record()
+        for _ in range(min(args.steps, 10)):
+            P.matvec(x, out=y_local, fmt="csr")
+        k1.record()
+        torch.cuda.synchronize()
+        alt_ms = k0.elapsed_time(k1) / min(args.steps, 10)
 
     # ---- e2e: host buffers through the public API -----------------------------------
     y_host = torch.empty(P.n_rows, dtype=torch.float64).pin_memory()
@@ -394,7 +405,8 @@ def run_ours(args):
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
         pt2 = {"value": st["raw_candidates_total"] / (float(pms[0]) * 1e-3), "unit": "PT2 candidates/s",
                "raw_candidates": st["raw_candidates_total"], "sources": ns, "ms": float(pms[0]),
-               "passes": st["passes"], "selected": int(sel.shape[0])}
+               "passes": st["passes"], "selected": int(sel.shape[0]),
+               "unique_candidates": st["unique_total"]}
 
     if rank != 0:
         if world > 1:
@@ -425,7 +437,8 @@ def run_ours(args):
         "config": workload_config(args, "matrix (26.7 GB at full size) is larger than L2; no flush needed"),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
-                     "kernel": "k_spmv_csr_vector<false,4>", "kernel_ms": kern_ms,
+                     "kernel": "k_spmv_sell<false,4>" if args.format == "sell" else "k_spmv_csr_vector<false,4>",
+                     "kernel_ms": kern_ms, "csr_vector_kernel_ms": alt_ms,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": which,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,
@@ -454,7 +467,8 @@ def main():
     ap.add_argument("--n-frozen", type=int, default=4)
     ap.add_argument("--n-active", type=int, default=14)
     ap.add_argument("--n-act-el", type=int, default=4)
-    ap.add_argument("--sort-rows", action="store_true", help="also sort CSR rows by column")
+    ap.add_argument("--no-sort-rows", action="store_true", help="leave CSR rows in enumeration order")
+    ap.add_argument("--format", default="sell", choices=["sell", "csr"], help="SpMV storage format")
     ap.add_argument("--pt2-sources", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=256)

@@ -40,13 +40,16 @@ _SIGNATURES = {
     "fgk_csr_sort_rows": (ci, [i64, vp, vp, vp, ci, vp]),
     "fgk_spmv_f64": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_z": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
-    "fgk_pt2_create": (ci, [i64, ci, C.POINTER(vp)]),
+    "fgk_sell_fill": (ci, [i64, vp, vp, vp, vp, vp, vp, ci, vp]),
+    "fgk_spmv_sell_f64": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
+    "fgk_spmv_sell_z": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
+    "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, vp, ci, C.POINTER(vp)]),
     "fgk_pt2_destroy": (ci, [vp]),
     "fgk_pt2_reset": (ci, [vp, vp]),
     "fgk_pt2_accumulate": (ci, [vp, vp, vp, vp, vp, i64, ci, ci, ci, vp]),
     "fgk_pt2_merge": (ci, [vp, vp, vp, i64, ci, vp]),
     "fgk_pt2_count": (ci, [vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(ci)]),
-    "fgk_pt2_export": (ci, [vp, vp, i64, dbl, vp, vp, vp, vp, vp, vp]),
+    "fgk_pt2_export": (ci, [vp, vp, i64, dbl, vp, vp, vp, vp, C.POINTER(i64), vp]),
 }
 
 

@@ -141,9 +141,8 @@ __device__ __forceinline__ bool set_has(const u64* set, u64 mask, u64 w)
     }
 }
 
-__device__ __forceinline__ int index_find(const IndexView& I, fgk_det o)
+__device__ __forceinline__ int index_find_h(const IndexView& I, fgk_det o, u64 h)
 {
-    u64 h = det_hash(o.a, o.b);
     u64 tag = h >> 32, slot = h & I.mask;
     while (true) {
         u64 e = __ldg(I.table + slot);
@@ -157,6 +156,11 @@ __device__ __forceinline__ int index_find(const IndexView& I, fgk_det o)
     }
 }
 
+__device__ __forceinline__ int index_find(const IndexView& I, fgk_det o)
+{
+    return index_find_h(I, o, det_hash(o.a, o.b));
+}
+
 // cheap necessary conditions first (alpha / beta string sets are small and
 // L1-resident), then the full-key probe.  cls tells which words changed.
 __device__ __forceinline__ int index_find_filtered(const IndexView& I, fgk_det o, int cls)
@@ -164,6 +168,13 @@ __device__ __forceinline__ int index_find_filtered(const IndexView& I, fgk_det o
     if (cls != 1 && cls != 3) { if (!set_has(I.aset, I.amask, o.a)) return -1; }
     if (cls != 0 && cls != 2) { if (!set_has(I.bset, I.bmask, o.b)) return -1; }
     return index_find(I, o);
+}
+
+__device__ __forceinline__ int index_find_filtered_h(const IndexView& I, fgk_det o, u64 h, int cls)
+{
+    if (cls != 1 && cls != 3) { if (!set_has(I.aset, I.amask, o.a)) return -1; }
+    if (cls != 0 && cls != 2) { if (!set_has(I.bset, I.bmask, o.b)) return -1; }
+    return index_find_h(I, o, h);
 }
 
 __device__ __forceinline__ double warp_sum(double v)

@@ -10,13 +10,6 @@
 // (:527-548): diagonal of every candidate and coupling^2 / (|E - E_x| + 1e-10).
 #include "fgk_internal.cuh"
 
-static u64 pow2_at_least(u64 x)
-{
-    u64 p = 1;
-    while (p < x) p <<= 1;
-    return p;
-}
-
 __device__ __forceinline__ void atomic_max_abs(double* addr, double v)
 {
     // non-negative doubles order like their bit patterns
@@ -25,9 +18,8 @@ __device__ __forceinline__ void atomic_max_abs(double* addr, double v)
 }
 
 // insert-or-accumulate; returns false on pool overflow
-__device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, double val, int mode)
+__device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, double val, int mode)
 {
-    u64 h = det_hash(o.a, o.b);
     u64 tag = h >> 32, slot = h & W.mask;
     long long mine = -1;        // pool slot this thread allocated (at most one)
     bool ok = true;
@@ -67,18 +59,51 @@ __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, double v
     return ok;
 }
 
+// work unit = (source, split): the 32-wide index chunks of one source's excitation
+// space are dealt round-robin to `n_split` warps, so that a few thousand sources
+// (each with 5e4 .. 3e5 connections) still fill 148 SMs x 64 warps.
+template <class FS, class FD>
+__device__ __forceinline__ void warp_enumerate_split(const DetCtx& c, int lane, int split, int n_split,
+                                                     FS&& fs, FD&& fd)
+{
+    int chunk = 0;
+    for (int t0 = 0; t0 < c.n_s; t0 += 32, chunk++) {
+        if (chunk % n_split != split) continue;
+        int t = t0 + lane, p = 0, q = 0;
+        bool va = false, vb = false;
+        if (t < c.n_s) decode_single(c, t, p, q, va, vb);
+        fs(va, vb, p, q);
+    }
+#pragma unroll 1
+    for (int st = 2; st <= 4; st++) {
+        const int size = st == 2 ? c.n_aa : (st == 3 ? c.n_bb : c.n_ab);
+        for (int t0 = 0; t0 < size; t0 += 32, chunk++) {
+            if (chunk % n_split != split) continue;
+            int t = t0 + lane;
+            Excitation x;
+            x.cls = st; x.h0 = x.h1 = x.e0 = x.e1 = 0;
+            bool valid = t < size;
+            if (valid) decode_double(c, st, t, x);
+            fd(valid, x);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FGK_BLOCK)
 k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_idx,
-                 const double* __restrict__ coeff, i64 n_src, int mode, unsigned n_pass,
+                 const double* __restrict__ coeff, i64 n_src, int n_split, int mode, unsigned n_pass,
                  unsigned pass_id)
 {
     __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
     const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
+    const i64 n_units = n_src * n_split;
     LdgF ldf;
     i64 tested = 0;
-    for (i64 sidx = warp0; sidx < n_src; sidx += nwarps) {
+    for (i64 unit = warp0; unit < n_units; unit += nwarps) {
+        const i64 sidx = unit / n_split;
+        const int split = (int)(unit - sidx * n_split);
         const i64 j = __ldg(src_idx + sidx);
         const double cj = __ldg(coeff + sidx);
         ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + j);
@@ -90,13 +115,14 @@ k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_
             float el;
             if (!ket_element(H, d, x, ldf, el)) return;          // reference filter
             fgk_det o = apply_excitation(d, c.n, x);
-            if (n_pass > 1 && (unsigned)((det_hash(o.a, o.b) >> 40) % n_pass) != pass_id) return;
+            const u64 h = det_hash(o.a, o.b);
+            if (n_pass > 1 && (unsigned)((h >> 40) % n_pass) != pass_id) return;
             tested++;
-            if (index_find_filtered(I, o, x.cls) >= 0) return;   // in the basis (:513)
-            pt2_upsert(W, o, cj * (double)el, mode);
+            if (index_find_filtered_h(I, o, h, x.cls) >= 0) return;   // in the basis (:513)
+            pt2_upsert(W, o, h, cj * (double)el, mode);
         };
-        warp_enumerate(
-            c, lane,
+        warp_enumerate_split(
+            c, lane, split, n_split,
             [&](bool va, bool vb, int p, int q) {
                 Excitation x;
                 x.h0 = q; x.e0 = p; x.h1 = 0; x.e1 = 0;
@@ -117,66 +143,71 @@ k_pt2_merge(Pt2View W, const fgk_det* __restrict__ dets, const double* __restric
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
         ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + i);
         fgk_det o = {d.x, d.y};
-        pt2_upsert(W, o, __ldg(vals + i), mode);
+        pt2_upsert(W, o, det_hash(o.a, o.b), __ldg(vals + i), mode);
     }
 }
 
+// live candidates are compacted to the front of the outputs (order is not
+// deterministic; every consumer treats them as a set); counters[3] = live count.
 __global__ void __launch_bounds__(256)
 k_pt2_export(HamView H, bool have_h, Pt2View W, i64 n_slots, double energy,
              fgk_det* __restrict__ out_dets, double* __restrict__ out_coupling,
-             double* __restrict__ out_diag, double* __restrict__ out_importance,
-             uint8_t* __restrict__ out_valid)
+             double* __restrict__ out_diag, double* __restrict__ out_importance)
 {
     LdgD ldd;
-    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_slots; k += (i64)gridDim.x * blockDim.x) {
-        ulonglong2 d = reinterpret_cast<const ulonglong2*>(W.keys)[k];
-        bool dead = (d.x == FGK_EMPTY && d.y == FGK_EMPTY);
-        double cpl = W.sums[k];
-        if (out_dets) reinterpret_cast<ulonglong2*>(out_dets)[k] = d;
-        if (out_coupling) out_coupling[k] = dead ? 0.0 : cpl;
-        if (out_valid) out_valid[k] = dead ? 0 : 1;
+    const int lane = threadIdx.x & 31;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 rounds = (n_slots + stride - 1) / stride;
+    for (i64 it = 0; it < rounds; it++) {
+        const i64 k = it * stride + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool live = false;
+        ulonglong2 d = make_ulonglong2(0, 0);
+        if (k < n_slots) {
+            d = reinterpret_cast<const ulonglong2*>(W.keys)[k];
+            live = !(d.x == FGK_EMPTY && d.y == FGK_EMPTY);
+        }
+        unsigned b = __ballot_sync(0xffffffffu, live);
+        if (!b) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(W.counters + 3, (unsigned long long)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!live) continue;
+        const i64 o = (i64)base + __popc(b & ((1u << lane) - 1u));
+        const double cpl = W.sums[k];
+        if (out_dets) reinterpret_cast<ulonglong2*>(out_dets)[o] = d;
+        if (out_coupling) out_coupling[o] = cpl;
         if (have_h) {
-            double ex = 0.0, imp = -1.0;
-            if (!dead) {
-                fgk_det dd = {d.x, d.y};
-                ex = diag_element(H, dd, ldd);
-                imp = cpl * cpl / (fabs(energy - ex) + 1e-10);   // residual_expansion.py:547-548
-            }
-            if (out_diag) out_diag[k] = ex;
-            if (out_importance) out_importance[k] = imp;
+            fgk_det dd = {d.x, d.y};
+            double ex = diag_element(H, dd, ldd);
+            if (out_diag) out_diag[o] = ex;
+            if (out_importance) out_importance[o] = cpl * cpl / (fabs(energy - ex) + 1e-10);   // :547-548
         }
     }
 }
 
-extern "C" int fgk_pt2_create(int64_t capacity, int device, fgk_pt2_t* out)
+extern "C" int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* keys,
+                              double* sums, uint64_t* counters, int device, fgk_pt2_t* out)
 {
-    if (!out || capacity < 1) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: bad argument");
+    if (!out || capacity < 1 || !table || !keys || !sums || !counters)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: bad argument");
     if (capacity >= (1ll << 32) - 1) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_pt2_create: capacity >= 2^32");
-    FGK_CUDA(cudaSetDevice(device));
+    if (table_slots < 2 || (table_slots & (table_slots - 1)) || table_slots < capacity)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: table_slots must be a power of two >= capacity");
+    if ((uintptr_t)keys & 15) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: keys must be 16-byte aligned");
     fgk_pt2* P = new fgk_pt2();
     P->device = device;
-    u64 tsize = pow2_at_least((u64)capacity * 2 < 1024 ? 1024 : (u64)capacity * 2);
     P->v.capacity = capacity;
-    P->v.mask = tsize - 1;
-    P->v.table = nullptr; P->v.keys = nullptr; P->v.sums = nullptr; P->v.counters = nullptr;
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&P->v.table, tsize * sizeof(u64))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&P->v.keys, (size_t)capacity * sizeof(fgk_det))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&P->v.sums, (size_t)capacity * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&P->v.counters, 4 * sizeof(unsigned long long))) != cudaSuccess) {
-        cudaFree(P->v.table); cudaFree(P->v.keys); cudaFree(P->v.sums); cudaFree(P->v.counters);
-        delete P;
-        return fgk_fail(FGK_ERR_CUDA, "fgk_pt2_create: cudaMalloc -> %s", cudaGetErrorString(e));
-    }
+    P->v.mask = (u64)table_slots - 1;
+    P->v.table = (u64*)table;
+    P->v.keys = (fgk_det*)keys;
+    P->v.sums = sums;
+    P->v.counters = (unsigned long long*)counters;
     *out = P;
-    return fgk_pt2_reset(P, nullptr);
+    return FGK_OK;
 }
 
 extern "C" int fgk_pt2_destroy(fgk_pt2_t ws)
 {
-    if (!ws) return FGK_OK;
-    cudaSetDevice(ws->device);
-    cudaFree(ws->v.table); cudaFree(ws->v.keys); cudaFree(ws->v.sums); cudaFree(ws->v.counters);
     delete ws;
     return FGK_OK;
 }
@@ -203,11 +234,15 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
     if (h->device != idx->device || h->device != ws->device)
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: device mismatch");
     FGK_CUDA(cudaSetDevice(h->device));
-    i64 need = (n_src + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
+    const i64 resident_warps = (i64)fgk_sm_count(h->device) * 64;
+    i64 n_split = (4 * resident_warps + n_src - 1) / n_src;     // >= 4 waves of work units
+    if (n_split < 1) n_split = 1;
+    if (n_split > 256) n_split = 256;
+    i64 need = (n_src * n_split + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
     i64 cap = (i64)fgk_sm_count(h->device) * 8;
     int grid = (int)(need < cap ? need : cap);
     k_pt2_accumulate<<<grid, FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, mode, (unsigned)n_pass,
+        h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, (unsigned)n_pass,
         (unsigned)pass_id);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
@@ -247,18 +282,24 @@ extern "C" int fgk_pt2_count(fgk_pt2_t ws, void* stream, int64_t* n_slots, int64
 
 extern "C" int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy,
                               uint64_t* out_dets, double* out_coupling, double* out_diag,
-                              double* out_importance, uint8_t* out_valid, void* stream)
+                              double* out_importance, int64_t* n_live, void* stream)
 {
     if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_export: null handle");
-    if (n_slots == 0) return FGK_OK;
+    if (n_slots == 0) { if (n_live) *n_live = 0; return FGK_OK; }
     if (n_slots < 0 || n_slots > ws->v.capacity) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_export: bad n_slots");
     FGK_CUDA(cudaSetDevice(ws->device));
     HamView hv;
     if (h) hv = h->v; else { hv = HamView(); }
     i64 need = (n_slots + 255) / 256, cap = (i64)fgk_sm_count(ws->device) * 8;
-    k_pt2_export<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+    cudaStream_t st = (cudaStream_t)stream;
+    FGK_CUDA(cudaMemsetAsync(ws->v.counters + 3, 0, sizeof(unsigned long long), st));
+    k_pt2_export<<<(int)(need < cap ? need : cap), 256, 0, st>>>(
         hv, h != nullptr, ws->v, n_slots, energy, (fgk_det*)out_dets, out_coupling, out_diag,
-        out_importance, out_valid);
+        out_importance);
     FGK_LAUNCH_CHECK();
+    unsigned long long live = 0;
+    FGK_CUDA(cudaMemcpyAsync(&live, ws->v.counters + 3, sizeof(live), cudaMemcpyDeviceToHost, st));
+    FGK_CUDA(cudaStreamSynchronize(st));
+    if (n_live) *n_live = (int64_t)live;
     return FGK_OK;
 }

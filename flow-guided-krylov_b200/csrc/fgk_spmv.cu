@@ -35,6 +35,7 @@ struct Acc<false> {
     __device__ __forceinline__ void fma(double v, const double* x, int c) { re = ::fma(v, __ldg(x + c), re); }
     __device__ __forceinline__ void reduce() { re = warp_sum(re); }
     __device__ __forceinline__ void store(double* y, i64 r) const { y[r] = re; }
+    static __device__ __forceinline__ double imag(const Acc&) { return 0.0; }
 };
 template <>
 struct Acc<true> {
@@ -51,6 +52,7 @@ struct Acc<true> {
     {
         reinterpret_cast<double2*>(y)[r] = make_double2(re, im);
     }
+    static __device__ __forceinline__ double imag(const Acc& a) { return a.im; }
 };
 
 template <bool CPLX, int UNROLL>
@@ -105,6 +107,8 @@ static int launch_spmv(int64_t n_rows, const int64_t* row_ptr, const int32_t* co
 {
     if (n_rows == 0) return FGK_OK;
     if (!row_ptr || !x || !y || n_rows < 0) return fgk_fail(FGK_ERR_ARG, "fgk_spmv: bad argument");
+    if (((uintptr_t)vals & 15) || ((uintptr_t)cols & 7))
+        return fgk_fail(FGK_ERR_ARG, "fgk_spmv: vals must be 16-byte and cols 8-byte aligned");
     FGK_CUDA(cudaSetDevice(device));
     i64 need = (n_rows + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
     i64 cap = (i64)fgk_sm_count(device) * 8;      // 8 resident CTAs of 8 warps = 64 warps / SM
@@ -125,4 +129,144 @@ extern "C" int fgk_spmv_z(int64_t n_rows, const int64_t* row_ptr, const int32_t*
                           const double* vals, const double* x, double* y, int device, void* stream)
 {
     return launch_spmv<true>(n_rows, row_ptr, cols, vals, x, y, device, stream);
+}
+
+// ======================================================================================
+// SELL-32: sliced ELLPACK with slice height 32 (one lane per row) and two entries per
+// lane per 128-bit load.  Entry k of row r = 32 s + l lives at
+//     slice_ptr[s] + ((k >> 1) * 32 + l) * 2 + (k & 1)
+// so a warp's value load is one fully coalesced, 16-byte aligned 512 B request and its
+// column load a 256 B one, with no per-row peel, no warp reduction and a coalesced y
+// store.  More importantly for this path, lane = row makes the 32 x-gathers of one
+// instruction fall into the SAME region of x: neighbouring basis determinants connect
+// to neighbouring columns (sorted rows), which the one-warp-per-row CSR kernel cannot
+// exploit (its 32 lanes walk 32 different columns of a single row).
+// One CTA of SELL_WARPS warps per slice; warp w takes pair-columns k2 = w, w+W, ... so
+// that the CTA streams one contiguous region; partial sums meet in shared memory.
+// The hardware CTA scheduler balances the ~n/32 slices over the SMs.
+// ======================================================================================
+static const int SELL_WARPS = 4;
+
+template <bool CPLX, int UNROLL>
+__global__ void __launch_bounds__(SELL_WARPS * 32)
+k_spmv_sell(i64 n_rows, const i64* __restrict__ slice_ptr, const int32_t* __restrict__ cols,
+            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y)
+{
+    __shared__ double s_part[SELL_WARPS][32][CPLX ? 2 : 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const i64 s = blockIdx.x;
+    const i64 base = __ldg(slice_ptr + s);
+    const i64 npair = (__ldg(slice_ptr + s + 1) - base) >> 6;      // pair-columns in this slice
+    const double* v0 = vals + base + 2 * lane;
+    const int32_t* c0 = cols + base + 2 * lane;
+    Acc<CPLX> acc;
+    i64 k2 = w;
+    for (; k2 + (i64)SELL_WARPS * (UNROLL - 1) < npair; k2 += (i64)SELL_WARPS * UNROLL) {
+        double2 v[UNROLL];
+        int2 c[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            v[u] = ld_stream_f64x2(v0 + (k2 + (i64)SELL_WARPS * u) * 64);
+            c[u] = ld_stream_s32x2(c0 + (k2 + (i64)SELL_WARPS * u) * 64);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            acc.fma(v[u].x, x, c[u].x);
+            acc.fma(v[u].y, x, c[u].y);
+        }
+    }
+    for (; k2 < npair; k2 += SELL_WARPS) {
+        double2 v = ld_stream_f64x2(v0 + k2 * 64);
+        int2 c = ld_stream_s32x2(c0 + k2 * 64);
+        acc.fma(v.x, x, c.x);
+        acc.fma(v.y, x, c.y);
+    }
+    s_part[w][lane][0] = acc.re;
+    if (CPLX) s_part[w][lane][CPLX ? 1 : 0] = Acc<CPLX>::imag(acc);
+    __syncthreads();
+    if (w == 0) {
+        const i64 r = s * 32 + lane;
+        if (r < n_rows) {
+            double re = 0.0, im = 0.0;
+#pragma unroll
+            for (int q = 0; q < SELL_WARPS; q++) {
+                re += s_part[q][lane][0];
+                if (CPLX) im += s_part[q][lane][CPLX ? 1 : 0];
+            }
+            if (CPLX) reinterpret_cast<double2*>(y)[r] = make_double2(re, im);
+            else y[r] = re;
+        }
+    }
+}
+
+// CSR -> SELL-32.  One CTA per slice; thread (pair-column k2, lane l) reads row l's
+// entries 2*k2, 2*k2+1 (L1 absorbs the row-strided reads) and writes coalesced.
+// Padding: value 0, column = 0.
+__global__ void __launch_bounds__(256)
+k_sell_fill(i64 n_rows, const i64* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+            const double* __restrict__ vals, const i64* __restrict__ slice_ptr,
+            int32_t* __restrict__ sc, double* __restrict__ sv)
+{
+    const i64 s = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const i64 base = slice_ptr[s];
+    const i64 npair = (slice_ptr[s + 1] - base) >> 6;
+    const i64 r = s * 32 + lane;
+    i64 rs = 0, len = 0;
+    if (r < n_rows) { rs = row_ptr[r]; len = row_ptr[r + 1] - rs; }
+    for (i64 k2 = w; k2 < npair; k2 += nw) {
+        double2 v = make_double2(0.0, 0.0);
+        int2 c = make_int2(0, 0);
+        i64 k = 2 * k2;
+        if (k < len) { v.x = vals[rs + k]; c.x = cols[rs + k]; }
+        if (k + 1 < len) { v.y = vals[rs + k + 1]; c.y = cols[rs + k + 1]; }
+        reinterpret_cast<double2*>(sv + base)[k2 * 32 + lane] = v;
+        reinterpret_cast<int2*>(sc + base)[k2 * 32 + lane] = c;
+    }
+}
+
+extern "C" int fgk_sell_fill(int64_t n_rows, const int64_t* row_ptr, const int32_t* cols,
+                             const double* vals, const int64_t* slice_ptr, int32_t* sell_cols,
+                             double* sell_vals, int device, void* stream)
+{
+    if (n_rows == 0) return FGK_OK;
+    if (!row_ptr || !slice_ptr || !sell_cols || !sell_vals || n_rows < 0)
+        return fgk_fail(FGK_ERR_ARG, "fgk_sell_fill: bad argument");
+    FGK_CUDA(cudaSetDevice(device));
+    i64 n_slices = (n_rows + 31) / 32;
+    k_sell_fill<<<(unsigned)n_slices, 256, 0, (cudaStream_t)stream>>>(
+        n_rows, (const i64*)row_ptr, cols, vals, (const i64*)slice_ptr, sell_cols, sell_vals);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+template <bool CPLX>
+static int launch_spmv_sell(int64_t n_rows, const int64_t* slice_ptr, const int32_t* cols,
+                            const double* vals, const double* x, double* y, int device, void* stream)
+{
+    if (n_rows == 0) return FGK_OK;
+    if (!slice_ptr || !cols || !vals || !x || !y || n_rows < 0)
+        return fgk_fail(FGK_ERR_ARG, "fgk_spmv_sell: bad argument");
+    if (((uintptr_t)vals & 15) || ((uintptr_t)cols & 7))
+        return fgk_fail(FGK_ERR_ARG, "fgk_spmv_sell: vals must be 16-byte and cols 8-byte aligned");
+    FGK_CUDA(cudaSetDevice(device));
+    i64 n_slices = (n_rows + 31) / 32;
+    k_spmv_sell<CPLX, 4><<<(unsigned)n_slices, SELL_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        n_rows, (const i64*)slice_ptr, cols, vals, x, y);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+extern "C" int fgk_spmv_sell_f64(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
+                                 const double* sell_vals, const double* x, double* y, int device,
+                                 void* stream)
+{
+    return launch_spmv_sell<false>(n_rows, slice_ptr, sell_cols, sell_vals, x, y, device, stream);
+}
+
+extern "C" int fgk_spmv_sell_z(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
+                               const double* sell_vals, const double* x, double* y, int device,
+                               void* stream)
+{
+    return launch_spmv_sell<true>(n_rows, slice_ptr, sell_cols, sell_vals, x, y, device, stream);
 }

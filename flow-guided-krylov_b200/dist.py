@@ -174,4 +174,5 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None):
     st = dict(st)
     st["raw_candidates_total"] = int(allreduce_scalar(float(st["raw_candidates"]), "sum", ham.device))
     st["unique_local"] = int(cand.shape[0])
+    st["unique_total"] = int(allreduce_scalar(float(cand.shape[0]), "sum", ham.device))
     return sel, simp, st

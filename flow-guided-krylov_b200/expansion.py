@@ -39,9 +39,21 @@ class Pt2Workspace:
     def __init__(self, capacity, device):
         self.capacity = int(capacity)
         self.device = device
+        slots = 1
+        while slots < 2 * self.capacity:
+            slots *= 2
+        slots = max(slots, 1024)
+        # caller-allocated (torch caching allocator): table, key pool, accumulators, counters
+        self._table = torch.empty(slots, dtype=torch.int64, device=device)
+        self._keys = torch.empty(self.capacity, 2, dtype=torch.int64, device=device)
+        self._sums = torch.empty(self.capacity, dtype=torch.float64, device=device)
+        self._counters = torch.zeros(4, dtype=torch.int64, device=device)
         h = C.c_void_p()
-        nat.check(nat.lib().fgk_pt2_create(self.capacity, nat.device_index(device), C.byref(h)))
+        nat.check(nat.lib().fgk_pt2_create(
+            self.capacity, slots, nat.ptr(self._table), nat.ptr(self._keys), nat.ptr(self._sums),
+            nat.ptr(self._counters), nat.device_index(device), C.byref(h)))
         self._h = h
+        self.reset()
 
     def __del__(self):
         try:
@@ -78,19 +90,19 @@ class Pt2Workspace:
         return ns.value, nr.value, bool(ov.value)
 
     def export(self, ham, n_slots, energy=0.0):
-        """-> (dets, coupling, diag, importance) of the live candidates."""
+        """-> (dets, coupling, diag, importance) of the live candidates (unordered)."""
         dev = self.device
         dets = torch.empty(n_slots, 2, dtype=torch.int64, device=dev)
         cpl = torch.empty(n_slots, dtype=torch.float64, device=dev)
         dg = torch.empty(n_slots, dtype=torch.float64, device=dev)
         imp = torch.empty(n_slots, dtype=torch.float64, device=dev)
-        valid = torch.empty(n_slots, dtype=torch.uint8, device=dev)
+        live = C.c_int64(0)
         nat.check(nat.lib().fgk_pt2_export(
             ham._h if ham is not None else None, self._h, n_slots, float(energy),
             nat.ptr(dets, torch.int64), nat.ptr(cpl, torch.float64), nat.ptr(dg, torch.float64),
-            nat.ptr(imp, torch.float64), nat.ptr(valid, torch.uint8), nat.stream_ptr(dev)))
-        m = valid.bool()
-        return dets[m], cpl[m], dg[m], imp[m]
+            nat.ptr(imp, torch.float64), C.byref(live), nat.stream_ptr(dev)))
+        m = live.value
+        return dets[:m], cpl[:m], dg[:m], imp[:m]
 
 
 def _key_sort_order(dets, n_orb):

@@ -53,7 +53,7 @@ class ProjectedH:
 
     @property
     def nnz(self):
-        return int(self.vals.numel())
+        return int(getattr(self, "_nnz", None) or self.vals.numel())
 
     def sort_rows(self):
         if not self.sorted_rows and self.nnz:
@@ -64,11 +64,52 @@ class ProjectedH:
         self.sorted_rows = True
         return self
 
-    def matvec(self, x, out=None):
-        """y = H[row_begin:row_end, :] @ x ; x real FP64 or complex128, length n."""
+    def to_sell(self, keep_csr=True):
+        """Build the SELL-32 copy used by matvec (fgk_sell_fill).  The CSR arrays stay
+        the canonical, reference-comparable form unless keep_csr=False."""
+        if getattr(self, "_sell", None) is not None:
+            return self
+        dev = self.cols.device
+        n_slices = (self.n_rows + 31) // 32
+        lens = torch.zeros(n_slices * 32, dtype=torch.int64, device=dev)
+        lens[: self.n_rows] = self.row_ptr[1:] - self.row_ptr[:-1]
+        width = lens.view(n_slices, 32).max(dim=1).values
+        width = (width + 1) // 2 * 2
+        slice_ptr = torch.zeros(n_slices + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(width * 32, 0, out=slice_ptr[1:])
+        total = int(slice_ptr[-1].item()) if n_slices else 0
+        sc = torch.empty(total, dtype=torch.int32, device=dev)
+        sv = torch.empty(total, dtype=torch.float64, device=dev)
+        if total:
+            nat.check(nat.lib().fgk_sell_fill(
+                self.n_rows, nat.ptr(self.row_ptr, torch.int64), nat.ptr(self.cols, torch.int32),
+                nat.ptr(self.vals, torch.float64), nat.ptr(slice_ptr, torch.int64),
+                nat.ptr(sc, torch.int32), nat.ptr(sv, torch.float64),
+                nat.device_index(self.device), nat.stream_ptr(self.device)))
+        self._sell = (slice_ptr, sc, sv)
+        self._nnz = self.nnz
+        if not keep_csr:
+            self._diag_cache = self.diagonal().clone()
+            self.cols = self.cols[:0]
+            self.vals = self.vals[:0]
+        return self
+
+    def matvec(self, x, out=None, fmt=None):
+        """y = H[row_begin:row_end, :] @ x ; x real FP64 or complex128, length n.
+        Uses the SELL-32 copy when to_sell() was called (fmt='csr' forces the CSR kernel)."""
         if x.shape[0] != self.n:
             raise ValueError(f"matvec: x has {x.shape[0]} entries, H has {self.n} columns")
         dev = nat.device_index(self.device)
+        sell = getattr(self, "_sell", None)
+        if sell is not None and fmt != "csr":
+            cplx = x.is_complex()
+            x = x.to(torch.complex128 if cplx else torch.float64).contiguous()
+            y = out if out is not None else torch.empty(self.n_rows, dtype=x.dtype, device=x.device)
+            fn = nat.lib().fgk_spmv_sell_z if cplx else nat.lib().fgk_spmv_sell_f64
+            nat.check(fn(self.n_rows, nat.ptr(sell[0], torch.int64), nat.ptr(sell[1], torch.int32),
+                         nat.ptr(sell[2], torch.float64), C.c_void_p(x.data_ptr()),
+                         C.c_void_p(y.data_ptr()), dev, nat.stream_ptr(self.device)))
+            return y
         if x.is_complex():
             if x.dtype != torch.complex128:
                 x = x.to(torch.complex128)
@@ -91,6 +132,8 @@ class ProjectedH:
 
     def diagonal(self):
         """the diagonal is the first entry of every row until sort_rows()."""
+        if getattr(self, "_diag_cache", None) is not None:
+            return self._diag_cache
         if self.sorted_rows:
             rows = torch.repeat_interleave(
                 torch.arange(self.row_begin, self.row_end, device=self.cols.device),

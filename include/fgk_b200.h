@@ -134,12 +134,32 @@ int fgk_spmv_f64(int64_t n_rows, const int64_t* row_ptr, const int32_t* cols, co
 int fgk_spmv_z(int64_t n_rows, const int64_t* row_ptr, const int32_t* cols, const double* vals,
                const double* x, double* y, int device, void* stream);
 
+/* SELL-32 flavour of the same product (sliced ELLPACK, slice height 32, entries
+ * stored in lane-interleaved pairs): entry k of row r = 32 s + l sits at
+ *   slice_ptr[s] + ((k >> 1) * 32 + l) * 2 + (k & 1).
+ * slice_ptr (n_slices + 1 entries, in elements) is sized by the caller:
+ * width_s = max row length in slice s rounded up to even, slice_ptr = scan(32 * width_s).
+ * fgk_sell_fill transposes CSR rows into it (padding: value 0, column 0). */
+int fgk_sell_fill(int64_t n_rows, const int64_t* row_ptr, const int32_t* cols, const double* vals,
+                  const int64_t* slice_ptr, int32_t* sell_cols, double* sell_vals, int device,
+                  void* stream);
+int fgk_spmv_sell_f64(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
+                      const double* sell_vals, const double* x, double* y, int device, void* stream);
+int fgk_spmv_sell_z(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
+                    const double* sell_vals, const double* x, double* y, int device, void* stream);
+
 /* ---- K7/K8 PT2 residual expansion --------------------------------------------------------
  * replaces SelectedCIExpander._find_important_configs (residual_expansion.py:451-554)
  * and ResidualBasedExpander._find_residual_configs (:174-253).
  * The workspace is a device hash map determinant -> FP64 accumulator with room for
- * `capacity` distinct candidates. */
-int fgk_pt2_create(int64_t capacity, int device, fgk_pt2_t* out);
+ * `capacity` distinct candidates.  All of its memory is the caller's:
+ *   table    uint64[table_slots]   (table_slots a power of two, >= 2*capacity advised)
+ *   keys     uint64[capacity][2]   (16-byte aligned)
+ *   sums     double[capacity]
+ *   counters uint64[4]
+ * fgk_pt2_create only wraps them in a handle; call fgk_pt2_reset before use. */
+int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* keys,
+                   double* sums, uint64_t* counters, int device, fgk_pt2_t* out);
 int fgk_pt2_destroy(fgk_pt2_t ws);
 int fgk_pt2_reset(fgk_pt2_t ws, void* stream);
 /* For every source s in [0,n_src): j = src_idx[s] (basis position), coefficient
@@ -157,12 +177,14 @@ int fgk_pt2_merge(fgk_pt2_t ws, const uint64_t* dets, const double* vals, int64_
 /* synchronises; host outputs: number of pool slots used (incl. dead ones), raw
  * candidates tested so far, overflow flag.  Returns FGK_ERR_CAPACITY on overflow. */
 int fgk_pt2_count(fgk_pt2_t ws, void* stream, int64_t* n_slots, int64_t* n_raw, int* overflow);
-/* for slot k in [0,n_slots): out_dets[k], out_coupling[k]; dead slots get
- * out_valid[k] = 0.  If h != NULL also out_diag[k] = <x|H|x> and
- * out_importance[k] = coupling^2 / (|energy - diag| + 1e-10)  (:547-548); dead slots -1. */
+/* The live candidates among the first n_slots pool slots, COMPACTED to the front of
+ * the outputs (buffers sized n_slots; order unspecified): determinant, accumulated
+ * coupling and, if h != NULL, out_diag = <x|H|x> and
+ * out_importance = coupling^2 / (|energy - diag| + 1e-10)  (:547-548).
+ * Synchronises; *n_live (host) = number of candidates written. */
 int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy, uint64_t* out_dets,
                    double* out_coupling, double* out_diag, double* out_importance,
-                   uint8_t* out_valid, void* stream);
+                   int64_t* n_live, void* stream);
 
 #ifdef __cplusplus
 }

@@ -223,6 +223,13 @@ def test_spmv_real_and_complex(fgk):
         yz = P.matvec(torch.from_numpy(z).cuda()).cpu().numpy()
         assert np.abs(y - orc.csr_matvec(indptr, indices, data, x)).max() < 1e-12
         assert np.abs(yz - orc.csr_matvec(indptr, indices, data, z)).max() < 1e-12
+        # SELL-32 copy of the same operator: same products
+        P.to_sell()
+        ys = P.matvec(torch.from_numpy(x).cuda()).cpu().numpy()
+        yzs = P.matvec(torch.from_numpy(z).cuda()).cpu().numpy()
+        assert np.abs(ys - orc.csr_matvec(indptr, indices, data, x)).max() < 1e-12
+        assert np.abs(yzs - orc.csr_matvec(indptr, indices, data, z)).max() < 1e-12
+        assert np.array_equal(P.matvec(torch.from_numpy(x).cuda(), fmt="csr").cpu().numpy(), y)
 
 
 @pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide"])
@@ -451,6 +458,10 @@ def test_large_cas_window_properties(fgk):
     a = float(torch.dot(y, S.matvec(x)))
     b = float(torch.dot(S.matvec(y), x))
     assert abs(a - b) < 1e-9 * max(1.0, abs(a))
+    # SELL-32 copy: same operator
+    ycsr = P.matvec(x)
+    P.to_sell()
+    assert float((P.matvec(x) - ycsr).abs().max()) < 1e-10
     # complex product = real product on real and imaginary parts
     z = torch.complex(x, y)
     yz = P.matvec(z)
