@@ -394,19 +394,28 @@ def run_ours(args):
         coeff = torch.zeros(n, dtype=torch.float64, device=dev)
         coeff[:ns] = torch.exp(-torch.arange(ns, dtype=torch.float64, device=dev) / (0.25 * ns))
         coeff /= torch.linalg.norm(coeff)
+        from flow_guided_krylov_b200.expansion import Pt2Workspace, default_pt2_capacity
+        n_local_src = -(-ns // world)
+        wsp = Pt2Workspace(default_pt2_capacity(H, n_local_src), dev)   # reused across sweeps, like an expander would
+        reps = 3
+        sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500, workspace=wsp)   # warm-up sweep
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
-        sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500)
+        for _ in range(reps):
+            sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500, workspace=wsp)
         p1.record()
         barrier()
-        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        pms = torch.tensor([p0.elapsed_time(p1) / reps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
         pt2 = {"value": st["raw_candidates_total"] / (float(pms[0]) * 1e-3), "unit": "PT2 candidates/s",
                "raw_candidates": st["raw_candidates_total"], "sources": ns, "ms": float(pms[0]),
                "passes": st["passes"], "selected": int(sel.shape[0]),
-               "unique_candidates": st["unique_total"]}
+               "unique_candidates": st["unique_total"],
+               "what": "enumerate -> filter -> hash-accumulate -> diagonal -> importance -> top-500, "
+                       "1 warm-up + 3 timed sweeps, workspace reused"}
+        del wsp
 
     if rank != 0:
         if world > 1:

@@ -149,16 +149,15 @@ def build_sharded_h(ham, dets, mode, index=None, sort_rows=True):
     return P, op
 
 
-def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None):
-    """Stage-3 selection with the sources sharded by row block and the candidates
-    owned by key hash.  Returns (selected dets, importances, stats); identical on all ranks."""
+def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None):
+    """Stage-3 selection with the significant sources dealt round-robin to the ranks and
+    the candidates owned by key hash.  Returns (selected dets, importances, stats); identical on all ranks."""
     from . import _native as nat
     from .expansion import Pt2Workspace, pt2_candidates
     mode = nat.PT2_SUM if mode is None else mode
     rank, ws = world()
-    n = len(index)
-    lo, hi = row_block(n, rank, ws)
-    cand, cpl, _, _, st = pt2_candidates(ham, index, coeffs, energy, mode=mode, src_range=(lo, hi))
+    cand, cpl, _, imp, st = pt2_candidates(ham, index, coeffs, energy, mode=mode,
+                                           src_shard=(rank, ws), workspace=workspace)
     if ws > 1:
         rd, rv = exchange_by_owner(cand, cpl)
         wsp = Pt2Workspace(max(1024, int(rd.shape[0]) + 16), ham.device)
@@ -167,8 +166,6 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None):
         if ov:
             raise RuntimeError("pt2_select_sharded: merge workspace overflow")
         cand, cpl, _, imp = wsp.export(ham, ns, energy)
-    else:
-        imp = cpl * cpl / ((energy - ham.diag_packed(cand)).abs() + 1e-10) if cand.shape[0] else cpl
     score = imp if mode == nat.PT2_SUM else cpl
     sel, simp = merge_topk(cand, score, k, ham.n_orbitals)
     st = dict(st)

@@ -137,16 +137,17 @@ def select_top_k(dets, score, k, n_orb):
 
 
 def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
-                   coeff_cut=1e-8, max_passes=64, src_range=None):
+                   coeff_cut=1e-8, max_passes=64, src_shard=None):
     """Phase 1+2 of _find_important_configs (residual_expansion.py:481-548) for the
-    sources of `index` (optionally only positions src_range=(lo,hi)).
+    sources of `index` (src_shard=(rank, world): only every world-th significant source,
+    the multi-GPU split -- the significant sources, not the rows, are what must balance).
     Returns (cand_dets, coupling, diag, importance, stats)."""
     dev = ham.device
     n = len(index)
     c32 = coeffs.to(dev).to(torch.float32)                         # :481
     src = torch.nonzero(c32.abs() > coeff_cut).squeeze(1)          # :489-490
-    if src_range is not None:
-        src = src[(src >= src_range[0]) & (src < src_range[1])]
+    if src_shard is not None:
+        src = src[src_shard[0]::src_shard[1]]
     cj = c32[src].double()
     stats = dict(n_sources=int(src.numel()), raw_candidates=0, passes=1)
     empty = (torch.empty(0, 2, dtype=torch.int64, device=dev),) + tuple(
@@ -155,10 +156,7 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
         return empty + (stats,)
     ws = workspace
     if ws is None:
-        n_conn = _raw_connections_per_det(ham)
-        free = nat.device_info(dev)["free_bytes"]
-        cap = int(min(max(4096, 1.25 * src.numel() * n_conn), 0.5 * free / 40, 2 ** 31))
-        ws = Pt2Workspace(cap, dev)
+        ws = Pt2Workspace(default_pt2_capacity(ham, int(src.numel())), dev)
     n_pass = 1
     while True:
         outs, raw, ok = [], 0, True
@@ -181,6 +179,14 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
     if len(outs) == 1:
         return outs[0] + (stats,)
     return tuple(torch.cat([o[i] for o in outs]) for i in range(4)) + (stats,)
+
+
+def default_pt2_capacity(ham, n_sources):
+    """pool slots for a sweep over n_sources determinants: every raw connection could be a
+    distinct candidate; bounded by half of the free HBM (56 B per slot incl. table)."""
+    n_conn = _raw_connections_per_det(ham)
+    free = nat.device_info(ham.device)["free_bytes"]
+    return int(min(max(4096, 1.05 * n_sources * n_conn), 0.5 * free / 56, 2 ** 31))
 
 
 def _raw_connections_per_det(ham):

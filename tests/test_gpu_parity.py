@@ -481,3 +481,104 @@ def test_large_cas_window_properties(fgk):
             if i is not None:
                 assert col[i] == float(e)
         assert abs(col[j] - O.diag(cfg[j:j + 1])[0]) < TOL
+
+
+def test_config5_shape_pt2_96_sites(fgk):
+    """48 orbitals = 96 sites (beyond the reference's own 64-bit key):
+    PT2 candidates, couplings and importances against the oracle, incl. the multi-pass path."""
+    from helpers import synth_integrals
+    from oracle import oracle as orc
+    from itertools import combinations
+    n_orb, na, nb, n_froz, n_act = 48, 12, 12, 10, 6
+    h1, gg = synth_integrals(n_orb, seed=5)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, na + nb, n_orb, na, nb), "cuda:0")
+    O = orc.OracleHam(h1.astype(np.float32), gg.astype(np.float32), na, nb)
+    strings = []
+    for occ in combinations(range(n_froz, n_froz + n_act), na - n_froz):
+        c = np.zeros(n_orb, np.uint8)
+        c[:n_froz] = 1
+        c[list(occ)] = 1
+        strings.append(c)
+    basis = np.array([np.concatenate([a, b]) for a in strings for b in strings], np.uint8)
+    basis = np.unique(basis, axis=0)
+    n = len(basis)
+    rng = np.random.default_rng(3)
+    v = np.zeros(n)
+    src = rng.choice(n, 6, replace=False)
+    v[src] = rng.standard_normal(6)
+    E = -3.0
+    cand_o, _, c64, raw = O.pt2_candidates(basis, v)
+    imp_o = c64 ** 2 / (np.abs(E - O.diag(cand_o)) + 1e-10)
+    dets = H.pack(t64(basis))
+    idx = fgk.BasisIndex(dets)
+    for ws in (None, fgk.Pt2Workspace(len(cand_o) // 5, "cuda:0")):
+        cand, cpl, dg, imp, st = fgk.pt2_candidates(H, idx, torch.from_numpy(v).cuda(), E, workspace=ws)
+        assert st["raw_candidates"] == raw
+        got = {bytes(r): i for i, r in enumerate(unpack_np(dets_np(cand), n_orb))}
+        assert len(got) == len(cand_o) and all(bytes(r) in got for r in cand_o)
+        perm = np.array([got[bytes(r)] for r in cand_o])
+        assert np.abs(cpl.cpu().numpy()[perm] - c64).max() < 1e-12
+        assert np.allclose(imp.cpu().numpy()[perm], imp_o, rtol=1e-9, atol=1e-15)
+    assert st["passes"] > 1
+    sel, simp = fgk.select_top_k(cand, imp, 50, n_orb)
+    o_sel, o_imp, *_ = O.find_important_configs(basis, E, v, 50)
+    assert {bytes(r) for r in unpack_np(dets_np(sel), n_orb)} == {bytes(r) for r in o_sel}
+
+
+def test_config4_full_size_properties(fgk):
+    """BASELINE configs[3] at full size (1,002,001 determinants, 2.2e9 nonzeros): checked
+    through size-independent properties -- exact row lengths, SpMV linearity,
+    self-adjointness of the symmetrised operator, CSR == SELL-32, a converged Davidson
+    pair, and sampled columns against the oracle."""
+    from math import comb
+    sys_path_bench = __import__("os").path.dirname(__import__("os").path.dirname(__file__))
+    import sys
+    sys.path.insert(0, sys_path_bench)
+    from bench import synth_integrals as bench_integrals, cas_window_basis
+    free = torch.cuda.mem_get_info()[0]
+    if free < 90e9:
+        pytest.skip("needs ~60 GB of free HBM")
+    n_orb, na, nb = 32, 8, 8
+    h1, gg = bench_integrals(n_orb, 0)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, 16, n_orb, na, nb), "cuda:0")
+    dnp = cas_window_basis(n_orb, 4, 14, 4)
+    dets = torch.from_numpy(dnp.view(np.int64)).cuda()
+    n = dets.shape[0]
+    assert n == 1002001
+    P = H.projected_csr(dets, fgk.H_SYM, packed=True)
+    per_row = 1 + 2 * 4 * 10 + 2 * comb(4, 2) * comb(10, 2) + (4 * 10) ** 2
+    assert per_row == 2221
+    assert torch.all(P.row_ptr[1:] - P.row_ptr[:-1] == per_row)
+    assert P.nnz == n * per_row
+    # sorted, in-range, duplicate-free columns in sampled rows
+    for r in (0, 12345, n - 1):
+        c = P.cols[P.row_ptr[r]:P.row_ptr[r + 1]].long()
+        assert torch.all(c[1:] > c[:-1]) and int(c[0]) >= 0 and int(c[-1]) < n
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(n, dtype=torch.float64, generator=g).cuda()
+    y = torch.randn(n, dtype=torch.float64, generator=g).cuda()
+    hx, hy = P.matvec(x), P.matvec(y)
+    assert float((P.matvec(2.0 * x - 3.0 * y) - (2.0 * hx - 3.0 * hy)).abs().max()) < 1e-8
+    a, b = float(torch.dot(y, hx)), float(torch.dot(hy, x))
+    assert abs(a - b) < 1e-9 * max(1.0, abs(a))
+    P.to_sell()
+    assert float((P.matvec(x) - hx).abs().max()) < 1e-9
+    z = torch.complex(x, y)
+    hz = P.matvec(z)
+    assert float((hz.real - hx).abs().max()) < 1e-9 and float((hz.imag - hy).abs().max()) < 1e-9
+    w, v = fgk.lowest_eigenpairs(P, k=1, tol=1e-10)
+    res = P.matvec(v[:, 0].contiguous()) - w[0] * v[:, 0]
+    assert float(torch.linalg.norm(res)) < 1e-7
+    assert float(w[0]) <= float(P.diagonal().min()) + 1e-12          # variational
+    # sampled columns vs the oracle's connections of those kets (symmetric integrals: H_ij = H_ji pattern)
+    from oracle import oracle as orc
+    O = orc.OracleHam(h1.astype(np.float32), gg.astype(np.float32), na, nb)
+    for j in (0, 500123):
+        cfg_j = unpack_np(dnp[j:j + 1], n_orb)[0]
+        cc, ee = O.connections(cfg_j)
+        keys = pack_np(cc, n_orb)
+        hit = fgk.BasisIndex(dets).lookup(torch.from_numpy(keys.view(np.int64)).cuda()).cpu().numpy()
+        rows = hit[hit >= 0]
+        assert len(rows) == per_row - 1
+        col = P.cols[P.row_ptr[j]:P.row_ptr[j + 1]].cpu().numpy()     # row j of the symmetrised H
+        assert np.array_equal(np.sort(np.append(rows, j)), col)
