@@ -14,7 +14,7 @@ from .build import LIB
 _lib = None
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-H_RAW, H_SYM, H_DROP_ZEROS = 0, 1, 2
+H_RAW, H_SYM, H_DROP_ZEROS, H_FLAT_WALK = 0, 1, 2, 4
 PT2_SUM, PT2_MAXABS = 0, 1
 
 vp, i64, ci, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double

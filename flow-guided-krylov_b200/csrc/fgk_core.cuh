@@ -333,3 +333,32 @@ FGK_HD void decode_double(const DetCtx& c, int stage, int t, Excitation& x)
     tri_decode(nv, pp, k, l);
     x.h0 = occ[i]; x.h1 = occ[j]; x.e0 = virt[k]; x.e1 = virt[l];
 }
+
+// ---- excitation recovered from two strings of the same spin ------------------------
+// x = from ^ to.  popc(x) == 2: single (hole = the bit set in `from`, particle = the bit
+// set in `to`); popc(x) == 4: double, holes h0 < h1 and particles e0 < e1 in ORBITAL
+// order (orbital p lives in bit n-1-p, so the higher bit is the lower orbital).
+FGK_HD int fgk_ctz(u64 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+FGK_HD void single_from_strings(u64 from, u64 to, int n, int& h, int& e)
+{
+    u64 x = from ^ to;
+    h = n - 1 - (63 - fgk_clz(x & from));
+    e = n - 1 - (63 - fgk_clz(x & to));
+}
+
+FGK_HD void double_from_strings(u64 from, u64 to, int n, int& h0, int& h1, int& e0, int& e1)
+{
+    u64 x = from ^ to, hs = x & from, es = x & to;
+    h0 = n - 1 - (63 - fgk_clz(hs));
+    h1 = n - 1 - fgk_ctz(hs);
+    e0 = n - 1 - (63 - fgk_clz(es));
+    e1 = n - 1 - fgk_ctz(es);
+}

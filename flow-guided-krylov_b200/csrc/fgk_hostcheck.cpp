@@ -117,4 +117,87 @@ long hc_bra_row(void* h, const u64* basis, long n, long i, int mode, int* out_co
     return m;
 }
 
+// Structured bra-mode row (the k_projh2 strategy): string-set filtered singles lists,
+// doubles found either by enumeration + set test (scan = 0) or by scanning the list of
+// distinct strings (scan = 1), alpha-beta doubles as the product of the two singles lists.
+long hc_bra_row2(void* h, const u64* basis, long n, long i, int mode, int scan, int* out_cols,
+                 double* out_vals, long cap)
+{
+    HcHam* H = (HcHam*)h;
+    std::map<std::pair<u64, u64>, long> index;
+    std::map<u64, int> aset, bset;
+    for (long k = 0; k < n; k++) {
+        index[{basis[2 * k], basis[2 * k + 1]}] = k;
+        aset[basis[2 * k]] = 1; bset[basis[2 * k + 1]] = 1;
+    }
+    uint8_t buf[256];
+    DetCtx c;
+    fgk_det d = {basis[2 * i], basis[2 * i + 1]};
+    const int nn = H->V.n_orb;
+    detctx_fill_host(c, nn, d, buf);
+    long m = 0;
+    if (m < cap) { out_cols[m] = (int)i; out_vals[m] = diag_element(H->V, d, ldd_host); }
+    m++;
+    auto emit = [&](const Excitation& x) {
+        fgk_det o = apply_excitation(d, c.n, x);
+        auto it = index.find({o.a, o.b});
+        if (it == index.end()) return;
+        float vij = 0.f, vji = 0.f;
+        bool kij = bra_element(H->V, d, x, ldf_host, vij);
+        bool kji = (mode == 1) ? ket_element(H->V, d, x, ldf_host, vji) : false;
+        if (!kij && !kji) return;
+        double v = mode == 1 ? 0.5 * ((double)(kij ? vij : 0.f) + (double)(kji ? vji : 0.f))
+                             : (double)vij;
+        if (m < cap) { out_cols[m] = (int)it->second; out_vals[m] = v; }
+        m++;
+    };
+    std::vector<std::pair<int, int>> L[2];
+    for (int spin = 0; spin < 2; spin++) {
+        u64 w = spin ? d.b : d.a;
+        auto& set = spin ? bset : aset;
+        const uint8_t* occ = spin ? c.occ_b : c.occ_a;
+        const uint8_t* virt = spin ? c.virt_b : c.virt_a;
+        int no = spin ? c.nob : c.noa, nv = spin ? c.nvb : c.nva;
+        if (scan) {
+            for (auto& kv : set) {
+                u64 x = kv.first ^ w;
+                int pc = fgk_popc(x);
+                if (pc == 2) {
+                    int hh, ee;
+                    single_from_strings(w, kv.first, nn, hh, ee);
+                    L[spin].push_back({hh, ee});
+                } else if (pc == 4) {
+                    Excitation e; e.cls = 2 + spin;
+                    double_from_strings(w, kv.first, nn, e.h0, e.h1, e.e0, e.e1);
+                    emit(e);
+                }
+            }
+        } else {
+            for (int t = 0; t < no * nv; t++) {
+                int hh = occ[t / nv], ee = virt[t % nv];
+                u64 w2 = w ^ orb_bit(nn, hh) ^ orb_bit(nn, ee);
+                if (set.count(w2)) L[spin].push_back({hh, ee});
+            }
+            int size = spin ? c.n_bb : c.n_aa;
+            for (int t = 0; t < size; t++) {
+                Excitation e;
+                decode_double(c, 2 + spin, t, e);
+                fgk_det o = apply_excitation(d, nn, e);
+                if (set.count(spin ? o.b : o.a)) emit(e);
+            }
+        }
+    }
+    for (int spin = 0; spin < 2; spin++)
+        for (auto& he : L[spin]) {
+            Excitation e; e.cls = spin; e.h0 = he.first; e.e0 = he.second; e.h1 = e.e1 = 0;
+            emit(e);
+        }
+    for (auto& a : L[0])
+        for (auto& b : L[1]) {
+            Excitation e; e.cls = 4; e.h0 = a.first; e.e0 = a.second; e.h1 = b.first; e.e1 = b.second;
+            emit(e);
+        }
+    return m;
+}
+
 }  // extern "C"

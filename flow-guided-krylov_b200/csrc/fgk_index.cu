@@ -63,6 +63,17 @@ k_set_insert(const fgk_det* __restrict__ dets, i64 n, int which, u64* set, u64 m
     }
 }
 
+// compact the occupied slots of a word set into a dense list (order irrelevant: the
+// projected-H builder sorts its rows afterwards)
+__global__ void __launch_bounds__(256)
+k_set_compact(const u64* __restrict__ set, u64 size, u64* __restrict__ list, unsigned long long* counter)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (u64)gridDim.x * blockDim.x) {
+        u64 w = set[i];
+        if (w != FGK_EMPTY) list[atomicAdd(counter, 1ull)] = w;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_index_lookup(IndexView I, const fgk_det* __restrict__ q, i64 m, int32_t* __restrict__ out)
 {
@@ -128,6 +139,17 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
         k_set_insert<<<grid1d(n, device), 256, 0, st>>>(d, n, 1, I->bset, bsz - 1, d_cnt + 1);
         FGK_LAUNCH_CHECK();
     }
+    // dense lists of the distinct strings (scanned by the projected-H builder)
+    I->alist = I->blist = nullptr;
+    FGK_CUDA(cudaMalloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64)));
+    FGK_CUDA(cudaMalloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64)));
+    FGK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+    if (n > 0) {
+        k_set_compact<<<grid1d((i64)asz, device), 256, 0, st>>>(I->aset, asz, I->alist, d_cnt);
+        FGK_LAUNCH_CHECK();
+        k_set_compact<<<grid1d((i64)bsz, device), 256, 0, st>>>(I->bset, bsz, I->blist, d_cnt + 1);
+        FGK_LAUNCH_CHECK();
+    }
     FGK_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp);
     cudaFree(d_cnt);
@@ -144,6 +166,7 @@ extern "C" int fgk_index_destroy(fgk_index_t idx)
     if (!idx) return FGK_OK;
     cudaSetDevice(idx->device);
     cudaFree(idx->table); cudaFree(idx->aset); cudaFree(idx->bset);
+    cudaFree(idx->alist); cudaFree(idx->blist);
     delete idx;
     return FGK_OK;
 }

@@ -54,6 +54,7 @@ struct fgk_index {
     int device;
     IndexView v;
     u64 *table, *aset, *bset;
+    u64 *alist, *blist;             // the distinct alpha / beta strings, compact
     i64 n_alpha_strings, n_beta_strings;
 };
 

@@ -76,12 +76,194 @@ k_projh(HamView H, IndexView I, i64 row_begin, i64 row_end, int mode, i64* __res
     }
 }
 
+// ---- structured row builder -----------------------------------------------------------
+// The flat walk above visits every excitation of the row determinant (52,704 at 32
+// orbitals / 8+8 electrons) although only those whose alpha AND beta strings occur in the
+// basis can hit (2,220 for the CAS basis).  This kernel turns the string sets into the
+// loop structure itself:
+//   1. per spin, the list of single excitations whose target string is in the basis
+//      (found by enumeration + set probe, or -- when the basis has fewer distinct strings
+//      than the row has double excitations -- by one scan over the distinct strings,
+//      classifying each by popc(string ^ own): 2 = single, 4 = double);
+//   2. same-spin doubles: from the same scan (or enumeration + set probe);
+//   3. alpha-beta doubles: the product of the two singles lists -- the only candidates
+//      whose both strings are in the basis.
+// Only these survivors reach the full-key probe and the element evaluation.
+struct ProjLists {
+    const u64* alist; i64 na;      // distinct alpha strings of the basis
+    const u64* blist; i64 nb;
+    int scan_a, scan_b;            // 1: classify by scanning the list, 0: enumerate + probe the set
+};
+
+static const int SINGLE_LIST_CAP = 1024;   // n_occ * n_virt <= 32 * 32
+
+template <bool FILL>
+__global__ void __launch_bounds__(FGK_BLOCK)
+k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int mode,
+         i64* __restrict__ counts, const i64* __restrict__ row_ptr, int32_t* __restrict__ cols,
+         double* __restrict__ vals)
+{
+    __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
+    __shared__ unsigned short s_single[FGK_WARPS_PER_BLOCK][2][SINGLE_LIST_CAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
+    const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
+    const bool sym = (mode & FGK_H_SYM) != 0, drop0 = (mode & FGK_H_DROP_ZEROS) != 0;
+    const int n = H.n_orb;
+    LdgF ldf;
+    LdgD ldd;
+    for (i64 i = row_begin + warp0; i < row_end; i += nwarps) {
+        ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + i);
+        fgk_det d = {dv.x, dv.y};
+        DetCtx c;
+        warp_build_ctx(c, n, d, s_lists[wib], lane);
+        i64 pos = FILL ? row_ptr[i - row_begin] : 0;
+        if (FILL && lane == 0) {
+            cols[pos] = (int32_t)i;
+            vals[pos] = diag_element(H, d, ldd);
+        }
+        pos += 1;
+        // full-key probe + element of one candidate per lane; rank inside the row by ballot
+        auto emit = [&](bool valid, const Excitation& x) {
+            int j = -1;
+            double v = 0.0;
+            bool keep = false;
+            if (valid) {
+                fgk_det o = apply_excitation(d, n, x);
+                j = index_find(I, o);
+                if (j >= 0) {
+                    float vij = 0.f, vji = 0.f;
+                    bool kij = bra_element(H, d, x, ldf, vij);
+                    bool kji = sym ? ket_element(H, d, x, ldf, vji) : false;
+                    keep = kij || kji;
+                    v = sym ? 0.5 * ((double)(kij ? vij : 0.f) + (double)(kji ? vji : 0.f))
+                            : (double)vij;
+                    if (drop0 && v == 0.0) keep = false;
+                }
+            }
+            unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (FILL && keep) {
+                i64 o = pos + __popc(b & lt);
+                cols[o] = j;
+                vals[o] = v;
+            }
+            pos += __popc(b);
+        };
+        int n_single[2] = {0, 0};
+#pragma unroll 1
+        for (int spin = 0; spin < 2; spin++) {
+            const u64 w = spin ? d.b : d.a;
+            unsigned short* L = s_single[wib][spin];
+            int cnt = 0;
+            auto push = [&](bool ok, int hh, int ee) {
+                unsigned b = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    int o = cnt + __popc(b & lt);
+                    if (o < SINGLE_LIST_CAP) L[o] = (unsigned short)((hh << 8) | ee);
+                }
+                cnt += __popc(b);
+            };
+            const bool scan = spin ? PL.scan_b : PL.scan_a;
+            if (scan) {
+                const u64* list = spin ? PL.blist : PL.alist;
+                const i64 nl = spin ? PL.nb : PL.na;
+                for (i64 t0 = 0; t0 < nl; t0 += 32) {
+                    i64 t = t0 + lane;
+                    u64 w2 = t < nl ? __ldg(list + t) : w;
+                    int pc = __popcll(w2 ^ w);
+                    int hh = 0, ee = 0;
+                    if (pc == 2) single_from_strings(w, w2, n, hh, ee);
+                    push(pc == 2, hh, ee);
+                    Excitation x;
+                    x.cls = 2 + spin; x.h0 = x.h1 = x.e0 = x.e1 = 0;
+                    if (pc == 4) double_from_strings(w, w2, n, x.h0, x.h1, x.e0, x.e1);
+                    if (__any_sync(0xffffffffu, pc == 4)) emit(pc == 4, x);
+                }
+            } else {
+                const u64* set = spin ? I.bset : I.aset;
+                const u64 smask = spin ? I.bmask : I.amask;
+                const uint8_t* occ = spin ? c.occ_b : c.occ_a;
+                const uint8_t* virt = spin ? c.virt_b : c.virt_a;
+                const int no = spin ? c.nob : c.noa, nv = spin ? c.nvb : c.nva;
+                for (int t0 = 0; t0 < no * nv; t0 += 32) {
+                    int t = t0 + lane;
+                    bool ok = false;
+                    int hh = 0, ee = 0;
+                    if (t < no * nv) {
+                        hh = occ[t / nv]; ee = virt[t % nv];
+                        ok = set_has(set, smask, w ^ orb_bit(n, hh) ^ orb_bit(n, ee));
+                    }
+                    push(ok, hh, ee);
+                }
+                const int size = spin ? c.n_bb : c.n_aa;
+                for (int t0 = 0; t0 < size; t0 += 32) {
+                    int t = t0 + lane;
+                    Excitation x;
+                    x.cls = 2 + spin; x.h0 = x.h1 = x.e0 = x.e1 = 0;
+                    bool ok = false;
+                    if (t < size) {
+                        decode_double(c, 2 + spin, t, x);
+                        u64 w2 = w ^ orb_bit(n, x.h0) ^ orb_bit(n, x.h1) ^ orb_bit(n, x.e0) ^ orb_bit(n, x.e1);
+                        ok = set_has(set, smask, w2);
+                    }
+                    if (__any_sync(0xffffffffu, ok)) emit(ok, x);
+                }
+            }
+            n_single[spin] = cnt < SINGLE_LIST_CAP ? cnt : SINGLE_LIST_CAP;
+        }
+        __syncwarp();
+        // singles
+#pragma unroll 1
+        for (int spin = 0; spin < 2; spin++) {
+            const unsigned short* L = s_single[wib][spin];
+            for (int t0 = 0; t0 < n_single[spin]; t0 += 32) {
+                int t = t0 + lane;
+                Excitation x;
+                x.cls = spin; x.h0 = x.h1 = x.e0 = x.e1 = 0;
+                bool ok = t < n_single[spin];
+                if (ok) { unsigned short he = L[t]; x.h0 = he >> 8; x.e0 = he & 0xff; }
+                emit(ok, x);
+            }
+        }
+        // alpha-beta doubles: product of the two lists
+        for (int ia = 0; ia < n_single[0]; ia++) {
+            const unsigned short ha = s_single[wib][0][ia];
+            for (int t0 = 0; t0 < n_single[1]; t0 += 32) {
+                int t = t0 + lane;
+                Excitation x;
+                x.cls = 4; x.h0 = ha >> 8; x.e0 = ha & 0xff; x.h1 = x.e1 = 0;
+                bool ok = t < n_single[1];
+                if (ok) { unsigned short he = s_single[wib][1][t]; x.h1 = he >> 8; x.e1 = he & 0xff; }
+                emit(ok, x);
+            }
+        }
+        if (!FILL && lane == 0) counts[i - row_begin] = pos;
+        __syncwarp();
+    }
+}
+
 static int grid_rows(i64 rows, int device)
 {
     i64 need = (rows + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
     i64 cap = (i64)fgk_sm_count(device) * 8;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// scan the distinct-string list when it is shorter than the row's own enumeration
+static ProjLists proj_lists(fgk_ham_t h, fgk_index_t idx)
+{
+    ProjLists P;
+    P.alist = idx->alist; P.na = idx->n_alpha_strings;
+    P.blist = idx->blist; P.nb = idx->n_beta_strings;
+    auto c2 = [](i64 m) { return m * (m - 1) / 2; };
+    const i64 n = h->v.n_orb, na = h->v.n_alpha, nb = h->v.n_beta;
+    const i64 enum_a = na * (n - na) + c2(na) * c2(n - na);
+    const i64 enum_b = nb * (n - nb) + c2(nb) * c2(n - nb);
+    P.scan_a = P.na <= enum_a ? 1 : 0;
+    P.scan_b = P.nb <= enum_b ? 1 : 0;
+    return P;
 }
 
 extern "C" int fgk_projh_count(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end,
@@ -94,8 +276,13 @@ extern "C" int fgk_projh_count(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, 
     if (!counts) return fgk_fail(FGK_ERR_ARG, "fgk_projh_count: null counts");
     if (h->device != idx->device) return fgk_fail(FGK_ERR_ARG, "fgk_projh_count: device mismatch");
     FGK_CUDA(cudaSetDevice(h->device));
-    k_projh<false><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, idx->v, row_begin, row_end, mode, (i64*)counts, nullptr, nullptr, nullptr);
+    if (mode & FGK_H_FLAT_WALK)
+        k_projh<false><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+            h->v, idx->v, row_begin, row_end, mode, (i64*)counts, nullptr, nullptr, nullptr);
+    else
+        k_projh2<false><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+            h->v, idx->v, proj_lists(h, idx), row_begin, row_end, mode, (i64*)counts, nullptr, nullptr,
+            nullptr);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }
@@ -111,8 +298,13 @@ extern "C" int fgk_projh_fill(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, i
     if (!row_ptr || !cols || !vals) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill: null pointer");
     if (h->device != idx->device) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill: device mismatch");
     FGK_CUDA(cudaSetDevice(h->device));
-    k_projh<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, idx->v, row_begin, row_end, mode, nullptr, (const i64*)row_ptr, cols, vals);
+    if (mode & FGK_H_FLAT_WALK)
+        k_projh<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+            h->v, idx->v, row_begin, row_end, mode, nullptr, (const i64*)row_ptr, cols, vals);
+    else
+        k_projh2<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+            h->v, idx->v, proj_lists(h, idx), row_begin, row_end, mode, nullptr, (const i64*)row_ptr,
+            cols, vals);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }

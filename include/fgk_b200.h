@@ -50,6 +50,9 @@ extern "C" {
                            /*  skqd.py:725, molecular.py:921)                       */
 #define FGK_H_DROP_ZEROS 2 /* OR-able: skip entries whose value is exactly 0.0      */
                            /*  (what scipy csr_matrix(dense) does, skqd.py:783)     */
+#define FGK_H_FLAT_WALK 4  /* OR-able: build rows by the flat reference-order walk  */
+                           /*  over every excitation instead of the string-set      */
+                           /*  driven builder (same entries; cross-check / debug)   */
 
 /* PT2 accumulation flavours */
 #define FGK_PT2_SUM 0      /* signed coupling sum   (residual_expansion.py:515-520) */

@@ -160,6 +160,11 @@ def test_projected_h(fgk, name):
     pat = np.zeros((n, n), bool)
     pat[np.repeat(np.arange(n), np.diff(M.indptr)), M.indices] = True
     assert np.array_equal(pat & off, (S != 0) & off)
+    # the string-set driven builder (default) and the flat reference-order walk agree entry by entry
+    for mode in (fgk.H_RAW, fgk.H_SYM, fgk.H_SYM | fgk.H_DROP_ZEROS):
+        A = H.projected_csr(basis, mode)
+        B = H.projected_csr(basis, mode | fgk.H_FLAT_WALK)
+        assert torch.equal(A.row_ptr, B.row_ptr) and torch.equal(A.cols, B.cols) and torch.equal(A.vals, B.vals)
     # row blocks reproduce the full build
     if n > 4:
         Pf = H.projected_csr(basis, fgk.H_RAW).to_scipy().toarray()
@@ -458,6 +463,9 @@ def test_large_cas_window_properties(fgk):
     a = float(torch.dot(y, S.matvec(x)))
     b = float(torch.dot(S.matvec(y), x))
     assert abs(a - b) < 1e-9 * max(1.0, abs(a))
+    F = H.projected_csr(dets, fgk.H_RAW | fgk.H_FLAT_WALK, packed=True, index=P._index)
+    assert torch.equal(F.row_ptr, P.row_ptr) and torch.equal(F.cols, P.cols) and torch.equal(F.vals, P.vals)
+    del F
     # SELL-32 copy: same operator
     ycsr = P.matvec(x)
     P.to_sell()

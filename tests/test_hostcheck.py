@@ -98,3 +98,28 @@ def test_bra_rows_match_oracle_dense(name, mode):
         ref_pat[g["coo_rows"], g["coo_cols"]] = True
         assert np.array_equal(pattern & off, ref_pat & off)
     hostcheck().hc_ham_destroy(hc)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("scan", [0, 1])
+def test_structured_bra_rows_equal_flat_enumeration(name, mode, scan):
+    """the string-set driven row builder (k_projh2 strategy) produces exactly the entries of
+    the flat reference-order enumeration"""
+    g = load_golden("ham_" + name)
+    hc, H, n_orb = make(g)
+    basis = np.concatenate([g["basis"], g["dets"]])
+    basis = np.unique(basis, axis=0)
+    pk = pack_np(basis, n_orb)
+    n = len(basis)
+    for i in range(0, n, max(1, n // 25)):
+        cap = n + 4
+        c1, v1 = np.zeros(cap, np.int32), np.zeros(cap)
+        c2, v2 = np.zeros(cap, np.int32), np.zeros(cap)
+        m1 = hostcheck().hc_bra_row(hc, _p(pk), n, i, mode, _p(c1), _p(v1), cap)
+        m2 = hostcheck().hc_bra_row2(hc, _p(pk), n, i, mode, scan, _p(c2), _p(v2), cap)
+        assert m1 == m2
+        o1, o2 = np.argsort(c1[:m1], kind="stable"), np.argsort(c2[:m2], kind="stable")
+        assert np.array_equal(c1[:m1][o1], c2[:m2][o2])
+        assert np.array_equal(v1[:m1][o1], v2[:m2][o2])
+    hostcheck().hc_ham_destroy(hc)
