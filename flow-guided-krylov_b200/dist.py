@@ -149,27 +149,75 @@ def build_sharded_h(ham, dets, mode, index=None, sort_rows=True):
     return P, op
 
 
-def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None):
-    """Stage-3 selection with the significant sources dealt round-robin to the ranks and
-    the candidates owned by key hash.  Returns (selected dets, importances, stats); identical on all ranks."""
+def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None, coeff_cut=1e-8,
+                       max_passes=4096):
+    """Stage-3 selection on N GPUs.  The significant sources are dealt round-robin to the
+    ranks; every bucket pass does: local enumerate + hash pre-reduce -> all-to-all of
+    (determinant, partial coupling) to the key-hash owner -> owner merge + diagonal +
+    importance + local top-k; the per-rank top-k lists meet in one all-gather and the same
+    deterministic merge runs everywhere.  Returns (selected dets, scores, stats); identical
+    on all ranks.  With one rank this is expansion.pt2_select."""
     from . import _native as nat
-    from .expansion import Pt2Workspace, pt2_candidates
+    from .expansion import (Pt2Workspace, _raw_connections_per_det, default_pt2_capacity,
+                            pt2_select, select_top_k)
     mode = nat.PT2_SUM if mode is None else mode
     rank, ws = world()
-    cand, cpl, _, imp, st = pt2_candidates(ham, index, coeffs, energy, mode=mode,
-                                           src_shard=(rank, ws), workspace=workspace)
-    if ws > 1:
-        rd, rv = exchange_by_owner(cand, cpl)
-        wsp = Pt2Workspace(max(1024, int(rd.shape[0]) + 16), ham.device)
-        wsp.merge(rd, rv, mode)
-        ns, _, ov = wsp.count()
-        if ov:
-            raise RuntimeError("pt2_select_sharded: merge workspace overflow")
-        cand, cpl, _, imp = wsp.export(ham, ns, energy)
-    score = imp if mode == nat.PT2_SUM else cpl
-    sel, simp = merge_topk(cand, score, k, ham.n_orbitals)
-    st = dict(st)
-    st["raw_candidates_total"] = int(allreduce_scalar(float(st["raw_candidates"]), "sum", ham.device))
-    st["unique_local"] = int(cand.shape[0])
-    st["unique_total"] = int(allreduce_scalar(float(cand.shape[0]), "sum", ham.device))
-    return sel, simp, st
+    if ws == 1:
+        sel, sc, st = pt2_select(ham, index, coeffs, energy, k, workspace=workspace, mode=mode,
+                                 coeff_cut=coeff_cut, max_passes=max_passes)
+        st = dict(st)
+        st["raw_candidates_total"] = st["raw_candidates"]
+        st["unique_total"] = st["unique_candidates"]
+        return sel, sc, st
+    dev = ham.device
+    c32 = coeffs.to(dev).to(torch.float32)
+    src = torch.nonzero(c32.abs() > coeff_cut).squeeze(1)[rank::ws]
+    cj = c32[src].double()
+    n_src_max = int(allreduce_scalar(float(src.numel()), "max", dev))
+    wa = workspace if workspace is not None else Pt2Workspace(
+        max(4096, default_pt2_capacity(ham, max(1, n_src_max)) // 3), dev)
+    raw_ub = n_src_max * _raw_connections_per_det(ham)
+    n_pass = max(1, -(-raw_ub // (2 * wa.capacity)))
+    wb = None
+    while True:
+        keep_d, keep_s, raw, uniq, ok = [], [], 0, 0, True
+        for p in range(n_pass):
+            wa.reset()
+            if src.numel():
+                wa.accumulate(ham, index, src, cj, mode, n_pass, p)
+            ns, nr, ov = wa.count()
+            if allreduce_scalar(1.0 if ov else 0.0, "max", dev) > 0:
+                ok = False
+                break
+            raw += nr
+            d, cpl, _, _ = wa.export(None, ns, 0.0, want_diag=False)
+            rd, rv = exchange_by_owner(d, cpl)
+            del d, cpl
+            need = int(rd.shape[0]) + 16
+            if wb is None or wb.capacity < need:
+                wb = None
+                wb = Pt2Workspace(max(1024, int(1.25 * need)), dev)
+            else:
+                wb.reset()
+            wb.merge(rd, rv, mode)
+            del rd, rv
+            nsb, _, ovb = wb.count()
+            if ovb:
+                raise RuntimeError("pt2_select_sharded: merge workspace overflow")
+            want_c = mode != nat.PT2_SUM
+            d, cpl, _, imp = wb.export(ham, nsb, energy, want_coupling=want_c, want_diag=False)
+            uniq += int(d.shape[0])
+            sd, ss = select_top_k(d, imp if mode == nat.PT2_SUM else cpl, k, ham.n_orbitals)
+            keep_d.append(sd.clone())
+            keep_s.append(ss.clone())
+            del d, cpl, imp
+        if ok:
+            break
+        n_pass *= 2
+        if n_pass > max_passes:
+            raise RuntimeError(f"PT2 candidate set does not fit the workspaces in {max_passes} passes")
+    sel, sc = merge_topk(torch.cat(keep_d), torch.cat(keep_s), k, ham.n_orbitals)
+    st = dict(n_sources=int(src.numel()), raw_candidates=raw, passes=n_pass, unique_local=uniq)
+    st["raw_candidates_total"] = int(allreduce_scalar(float(raw), "sum", dev))
+    st["unique_total"] = int(allreduce_scalar(float(uniq), "sum", dev))
+    return sel, sc, st

@@ -89,20 +89,22 @@ class Pt2Workspace:
             nat.check(rc)
         return ns.value, nr.value, bool(ov.value)
 
-    def export(self, ham, n_slots, energy=0.0):
-        """-> (dets, coupling, diag, importance) of the live candidates (unordered)."""
+    def export(self, ham, n_slots, energy=0.0, want_coupling=True, want_diag=True):
+        """-> (dets, coupling, diag, importance) of the live candidates (unordered);
+        coupling / diag are None when not requested (saves 8 B per candidate each)."""
         dev = self.device
         dets = torch.empty(n_slots, 2, dtype=torch.int64, device=dev)
-        cpl = torch.empty(n_slots, dtype=torch.float64, device=dev)
-        dg = torch.empty(n_slots, dtype=torch.float64, device=dev)
+        cpl = torch.empty(n_slots, dtype=torch.float64, device=dev) if want_coupling else None
+        dg = torch.empty(n_slots, dtype=torch.float64, device=dev) if want_diag else None
         imp = torch.empty(n_slots, dtype=torch.float64, device=dev)
         live = C.c_int64(0)
         nat.check(nat.lib().fgk_pt2_export(
             ham._h if ham is not None else None, self._h, n_slots, float(energy),
-            nat.ptr(dets, torch.int64), nat.ptr(cpl, torch.float64), nat.ptr(dg, torch.float64),
+            nat.ptr(dets, torch.int64), nat.ptr(cpl), nat.ptr(dg),
             nat.ptr(imp, torch.float64), C.byref(live), nat.stream_ptr(dev)))
         m = live.value
-        return dets[:m], cpl[:m], dg[:m], imp[:m]
+        return (dets[:m], cpl[:m] if cpl is not None else None,
+                dg[:m] if dg is not None else None, imp[:m])
 
 
 def _key_sort_order(dets, n_orb):
@@ -183,10 +185,61 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
 
 def default_pt2_capacity(ham, n_sources):
     """pool slots for a sweep over n_sources determinants: every raw connection could be a
-    distinct candidate; bounded by half of the free HBM (56 B per slot incl. table)."""
+    distinct candidate; bounded by the free HBM (56 B per slot for table + pool, 24-40 B per
+    slot for the export buffers)."""
     n_conn = _raw_connections_per_det(ham)
     free = nat.device_info(ham.device)["free_bytes"]
-    return int(min(max(4096, 1.05 * n_sources * n_conn), 0.5 * free / 56, 2 ** 31))
+    return int(min(max(4096, 1.05 * n_sources * n_conn), 0.8 * free / 96, 2 ** 31))
+
+
+def pt2_select(ham, index, coeffs, energy, k, workspace=None, mode=nat.PT2_SUM, coeff_cut=1e-8,
+               max_passes=4096, src_shard=None):
+    """Streaming form of the selection: enumerate -> filter -> accumulate -> importance ->
+    top-k, keeping only k candidates per bucket pass, so candidate sets far beyond HBM
+    (config 5: ~3e10 raw connections) are processed exactly in n_pass sweeps.
+    Returns (selected dets, importances (or max |c.H|), stats)."""
+    dev = ham.device
+    c32 = coeffs.to(dev).to(torch.float32)
+    src = torch.nonzero(c32.abs() > coeff_cut).squeeze(1)
+    if src_shard is not None:
+        src = src[src_shard[0]::src_shard[1]]
+    cj = c32[src].double()
+    stats = dict(n_sources=int(src.numel()), raw_candidates=0, passes=1, unique_candidates=0)
+    if src.numel() == 0:
+        return (torch.empty(0, 2, dtype=torch.int64, device=dev),
+                torch.empty(0, dtype=torch.float64, device=dev), stats)
+    ws = workspace if workspace is not None else Pt2Workspace(
+        default_pt2_capacity(ham, int(src.numel())), dev)
+    # first guess: half of the raw connections are distinct candidates
+    raw_ub = int(src.numel()) * _raw_connections_per_det(ham)
+    n_pass = max(1, -(-raw_ub // (2 * ws.capacity)))
+    while True:
+        keep_d, keep_s, raw, uniq, ok = [], [], 0, 0, True
+        for p in range(n_pass):
+            ws.reset()
+            ws.accumulate(ham, index, src, cj, mode, n_pass, p)
+            ns, nr, ov = ws.count()
+            if ov:
+                ok = False
+                break
+            raw += nr
+            want_c = mode != nat.PT2_SUM
+            d, cpl, _, imp = ws.export(ham, ns, energy, want_coupling=want_c, want_diag=False)
+            uniq += int(d.shape[0])
+            sd, ss = select_top_k(d, imp if mode == nat.PT2_SUM else cpl, k, ham.n_orbitals)
+            keep_d.append(sd.clone())
+            keep_s.append(ss.clone())
+            del d, cpl, imp
+        if ok:
+            break
+        n_pass *= 2
+        if n_pass > max_passes:
+            raise RuntimeError(f"PT2 candidate set does not fit the workspace in {max_passes} passes")
+    stats.update(raw_candidates=raw, passes=n_pass, unique_candidates=uniq)
+    if n_pass == 1:
+        return keep_d[0], keep_s[0], stats
+    sd, ss = select_top_k(torch.cat(keep_d), torch.cat(keep_s), k, ham.n_orbitals)
+    return sd, ss, stats
 
 
 def _raw_connections_per_det(ham):
@@ -219,11 +272,9 @@ class SelectedCIExpander:
     # :451-554
     def _find_important_packed(self, dets, index, energy, v):
         H = self.hamiltonian
-        cand, cpl, dg, imp, st = pt2_candidates(H, index, v, energy)
+        sel, imp, st = pt2_select(H, index, v, energy, self.config.max_configs_per_iter)
         self.last_stats = st
-        if cand.shape[0] == 0:
-            return cand, imp
-        return select_top_k(cand, imp, self.config.max_configs_per_iter, H.n_orbitals)
+        return sel, imp
 
     def _find_important_configs(self, basis, energy, eigenvector):
         H = self.hamiltonian
