@@ -11,6 +11,9 @@
 //           excitations before the full-key probe.
 // Replaces the Python dict / set of molecular.py:501,512,
 // residual_expansion.py:445-449,513 and skqd.py:171-175,405-407.
+#include <algorithm>
+#include <vector>
+
 #include "fgk_internal.cuh"
 
 static u64 pow2_at_least(u64 x)
@@ -151,6 +154,16 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
         FGK_LAUNCH_CHECK();
     }
     FGK_CUDA(cudaStreamSynchronize(st));
+    // ascending order makes the builder's emission order deterministic (the atomic append
+    // above is not); the lists are small next to the basis, a host sort is enough
+    for (int which = 0; which < 2 && n > 0; which++) {
+        u64* dl = which ? I->blist : I->alist;
+        size_t m = (size_t)h_cnt[which];
+        std::vector<u64> hl(m);
+        FGK_CUDA(cudaMemcpy(hl.data(), dl, m * sizeof(u64), cudaMemcpyDeviceToHost));
+        std::sort(hl.begin(), hl.end());
+        FGK_CUDA(cudaMemcpy(dl, hl.data(), m * sizeof(u64), cudaMemcpyHostToDevice));
+    }
     cudaFree(tmp);
     cudaFree(d_cnt);
     I->v.dets = d; I->v.n = n;

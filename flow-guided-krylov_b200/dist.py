@@ -137,7 +137,7 @@ def allreduce_scalar(x: float, op="sum", device="cpu") -> float:
 
 
 # ---- engine-facing helpers (CUDA) ----------------------------------------------------------
-def build_sharded_h(ham, dets, mode, index=None, sort_rows=True):
+def build_sharded_h(ham, dets, mode, index=None, sort_rows=False):
     """each rank builds CSR rows of its block; returns (ProjectedH block, ShardedOperator)."""
     from .hamiltonian import BasisIndex
     rank, ws = world()

@@ -151,6 +151,7 @@ class ProjectedH:
 
     def to_scipy(self, dtype=np.float64):
         import scipy.sparse as sp
+        self.sort_rows()
         M = sp.csr_matrix((self.vals.cpu().numpy().astype(dtype), self.cols.cpu().numpy(),
                            self.row_ptr.cpu().numpy()), shape=(self.n_rows, self.n))
         return M
@@ -341,24 +342,36 @@ class MolecularHamiltonian:
         return self.get_connections_batch(configs)
 
     # ---- projected Hamiltonian (K4 + K5) ---------------------------------------------------
-    def projected_csr(self, basis, mode=nat.H_RAW, row_begin=0, row_end=None, sort_rows=True,
-                      index: Optional[BasisIndex] = None, packed=False) -> ProjectedH:
+    def projected_csr(self, basis, mode=nat.H_RAW, row_begin=0, row_end=None, sort_rows=False,
+                      index: Optional[BasisIndex] = None, packed=False, profile=False) -> ProjectedH:
         """CSR rows [row_begin,row_end) of <i|H|j> over `basis` (configs, or packed
-        words if packed=True).  mode: H_RAW | H_SYM [| H_DROP_ZEROS]."""
+        words if packed=True).  mode: H_RAW | H_SYM [| H_DROP_ZEROS].  Rows come in the
+        builder's (deterministic) emission order with the diagonal first; H.v does not
+        care.  sort_rows=True / .sort_rows() / .to_scipy() order them by column."""
         dets = basis if packed else self.pack(basis)
         idx = index if index is not None else BasisIndex(dets)
         n = len(idx)
         row_end = n if row_end is None else row_end
         rows = row_end - row_begin
         st = nat.stream_ptr(self.device)
+        import time as _time
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if profile else None
         counts = torch.empty(rows, dtype=torch.int64, device=self.device)
+        if profile:
+            ev[0].record()
         nat.check(nat.lib().fgk_projh_count(self._h, idx._h, row_begin, row_end, mode,
                                             nat.ptr(counts, torch.int64), st))
+        if profile:
+            ev[1].record()
         row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=self.device)
         torch.cumsum(counts, 0, out=row_ptr[1:])
         nnz = int(row_ptr[-1].item()) if rows else 0
+        t0 = _time.perf_counter()
         cols = torch.empty(nnz, dtype=torch.int32, device=self.device)
         vals = torch.empty(nnz, dtype=torch.float64, device=self.device)
+        t_alloc = _time.perf_counter() - t0
+        if profile:
+            ev[2].record()
         if nnz:
             nat.check(nat.lib().fgk_projh_fill(self._h, idx._h, row_begin, row_end, mode,
                                                nat.ptr(row_ptr, torch.int64),
@@ -366,6 +379,11 @@ class MolecularHamiltonian:
                                                nat.ptr(vals, torch.float64), st))
         P = ProjectedH(n, row_ptr, cols, vals, self.device, row_begin, row_end, mode)
         P._index = idx
+        if profile:
+            ev[3].record()
+            ev[3].synchronize()
+            P.build_profile = {"count_ms": ev[0].elapsed_time(ev[1]), "fill_ms": ev[2].elapsed_time(ev[3]),
+                               "alloc_ms": 1e3 * t_alloc}
         return P.sort_rows() if sort_rows else P
 
     @torch.no_grad()

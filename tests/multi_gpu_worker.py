@@ -30,8 +30,8 @@ def main():
     idx = fgk.BasisIndex(dets)
 
     # projected H: row blocks == rows of the full build; sharded H.v == full H.v
-    Pfull = H.projected_csr(dets, fgk.H_SYM, index=idx, packed=True)
-    Pblk, op = fd.build_sharded_h(H, dets, fgk.H_SYM, index=idx)
+    Pfull = H.projected_csr(dets, fgk.H_SYM, index=idx, packed=True, sort_rows=True)
+    Pblk, op = fd.build_sharded_h(H, dets, fgk.H_SYM, index=idx, sort_rows=True)
     lo, hi = fd.row_block(n, rank, world)
     assert torch.equal(Pblk.row_ptr, Pfull.row_ptr[lo:hi + 1] - Pfull.row_ptr[lo])
     assert torch.equal(Pblk.cols, Pfull.cols[Pfull.row_ptr[lo]:Pfull.row_ptr[hi]])

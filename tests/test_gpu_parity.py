@@ -162,8 +162,8 @@ def test_projected_h(fgk, name):
     assert np.array_equal(pat & off, (S != 0) & off)
     # the string-set driven builder (default) and the flat reference-order walk agree entry by entry
     for mode in (fgk.H_RAW, fgk.H_SYM, fgk.H_SYM | fgk.H_DROP_ZEROS):
-        A = H.projected_csr(basis, mode)
-        B = H.projected_csr(basis, mode | fgk.H_FLAT_WALK)
+        A = H.projected_csr(basis, mode, sort_rows=True)
+        B = H.projected_csr(basis, mode | fgk.H_FLAT_WALK, sort_rows=True)
         assert torch.equal(A.row_ptr, B.row_ptr) and torch.equal(A.cols, B.cols) and torch.equal(A.vals, B.vals)
     # row blocks reproduce the full build
     if n > 4:
@@ -445,7 +445,7 @@ def test_large_cas_window_properties(fgk):
     dets = torch.from_numpy(dets.reshape(-1, 2).view(np.int64)).cuda()
     n = dets.shape[0]
     assert n == comb(n_act, 4) ** 2
-    P = H.projected_csr(dets, fgk.H_RAW, packed=True)
+    P = H.projected_csr(dets, fgk.H_RAW, packed=True, sort_rows=True)
     # every row: diagonal + singles + same-spin doubles + alpha-beta doubles inside the window
     ne, nv = 4, n_act - 4
     per_row = 1 + 2 * ne * nv + 2 * comb(ne, 2) * comb(nv, 2) + (ne * nv) ** 2
@@ -463,7 +463,7 @@ def test_large_cas_window_properties(fgk):
     a = float(torch.dot(y, S.matvec(x)))
     b = float(torch.dot(S.matvec(y), x))
     assert abs(a - b) < 1e-9 * max(1.0, abs(a))
-    F = H.projected_csr(dets, fgk.H_RAW | fgk.H_FLAT_WALK, packed=True, index=P._index)
+    F = H.projected_csr(dets, fgk.H_RAW | fgk.H_FLAT_WALK, packed=True, index=P._index, sort_rows=True)
     assert torch.equal(F.row_ptr, P.row_ptr) and torch.equal(F.cols, P.cols) and torch.equal(F.vals, P.vals)
     del F
     # SELL-32 copy: same operator
@@ -553,7 +553,7 @@ def test_config4_full_size_properties(fgk):
     dets = torch.from_numpy(dnp.view(np.int64)).cuda()
     n = dets.shape[0]
     assert n == 1002001
-    P = H.projected_csr(dets, fgk.H_SYM, packed=True)
+    P = H.projected_csr(dets, fgk.H_SYM, packed=True, sort_rows=True)
     per_row = 1 + 2 * 4 * 10 + 2 * comb(4, 2) * comb(10, 2) + (4 * 10) ** 2
     assert per_row == 2221
     assert torch.all(P.row_ptr[1:] - P.row_ptr[:-1] == per_row)
