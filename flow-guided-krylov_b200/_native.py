@@ -43,6 +43,12 @@ _SIGNATURES = {
     "fgk_sell_fill": (ci, [i64, vp, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_sell_f64": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_sell_z": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
+    "fgk_peer_alloc": (ci, [C.c_size_t, ci, C.POINTER(vp), C.c_char_p]),
+    "fgk_peer_open": (ci, [C.c_char_p, ci, C.POINTER(vp)]),
+    "fgk_peer_close": (ci, [vp, ci]),
+    "fgk_peer_free": (ci, [vp, ci]),
+    "fgk_spmv_sell_f64_allgather": (ci, [i64, vp, vp, vp, vp, C.POINTER(vp), ci, i64, ci, vp]),
+    "fgk_peer_barrier": (ci, [C.POINTER(vp), ci, ci, C.c_uint64, vp, ci, vp]),
     "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, vp, ci, C.POINTER(vp)]),
     "fgk_pt2_destroy": (ci, [vp]),
     "fgk_pt2_reset": (ci, [vp, vp]),

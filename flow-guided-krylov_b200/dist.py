@@ -221,3 +221,117 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
     st["raw_candidates_total"] = int(allreduce_scalar(float(raw), "sum", dev))
     st["unique_total"] = int(allreduce_scalar(float(uniq), "sum", dev))
     return sel, sc, st
+
+
+# ---- H.v with the all-gather fused into the kernel (peer memory over NVLink) --------------------
+class _DevArray:
+    """view of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2}
+
+
+class FusedShardedOperator:
+    """Row-block sharded H with y = H x produced directly in every rank's next vector
+    buffer: fgk_spmv_sell_f64_allgather stores each y_r into the peer-mapped buffers of all
+    ranks while it streams the matrix, and fgk_peer_barrier closes the step -- no separate
+    collective.  Buffers ping-pong.  Real FP64 vectors (the Davidson / power-iteration side
+    of Stage 4); complex vectors use ShardedOperator."""
+
+    def __init__(self, P, group=None):
+        import ctypes as C
+        from . import _native as nat
+        self.P = P.to_sell()
+        self.n = P.n
+        self.rank, self.world = world()
+        self.dev = nat.device_index(P.device)
+        self.device = P.device
+        self.row_begin, self.row_end = P.row_begin, P.row_end
+        L = nat.lib()
+        nbytes = 8 * self.n
+        own, handles = [], []
+        for _ in range(3):                     # two vector buffers + the flag array
+            ptr, h = C.c_void_p(), C.create_string_buffer(64)
+            nat.check(L.fgk_peer_alloc(nbytes if len(own) < 2 else 8 * 64, self.dev, C.byref(ptr), h))
+            own.append(ptr.value)
+            handles.append(h.raw)
+        self._own = own
+        allh = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(allh, handles, group=group)
+        else:
+            allh = [handles]
+        self._opened = []
+        ptrs = [[0] * self.world for _ in range(3)]
+        for p in range(self.world):
+            for b in range(3):
+                if p == self.rank:
+                    ptrs[b][p] = own[b]
+                else:
+                    q = C.c_void_p()
+                    nat.check(L.fgk_peer_open(allh[p][b], self.dev, C.byref(q)))
+                    ptrs[b][p] = q.value
+                    self._opened.append(q.value)
+        VP = C.c_void_p * self.world
+        self._bufs = [VP(*ptrs[0]), VP(*ptrs[1])]
+        self._flags = VP(*ptrs[2])
+        self._views = [torch.as_tensor(_DevArray(own[b], self.n), device=P.device) for b in range(2)]
+        self._err = torch.zeros(1, dtype=torch.int64, device=P.device)
+        self._epoch = 0
+        self._cur = 0
+        self._diag = None
+        if self.world > 1:
+            dist.barrier(group=group)          # every rank has mapped every buffer
+
+    def close(self):
+        from . import _native as nat
+        L = nat.lib()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        for q in getattr(self, "_opened", []):
+            L.fgk_peer_close(q, self.dev)
+        self._opened = []
+        self._views = []
+        for q in getattr(self, "_own", []):
+            L.fgk_peer_free(q, self.dev)
+        self._own = []
+
+    def current(self):
+        """the full current vector on this rank (a view: valid until the step after next)."""
+        return self._views[self._cur]
+
+    def load(self, x):
+        self._views[self._cur].copy_(x)
+
+    def step(self):
+        """cur <- H cur on every rank; returns the new current vector (view)."""
+        import ctypes as C
+        from . import _native as nat
+        L = nat.lib()
+        st = nat.stream_ptr(self.device)
+        sp, sc, sv = self.P._sell
+        nxt = 1 - self._cur
+        nat.check(L.fgk_spmv_sell_f64_allgather(
+            self.P.n_rows, nat.ptr(sp, torch.int64), nat.ptr(sc, torch.int32), nat.ptr(sv, torch.float64),
+            C.c_void_p(self._own[self._cur]), self._bufs[nxt], self.world, self.row_begin, self.dev, st))
+        self._epoch += 1
+        nat.check(L.fgk_peer_barrier(self._flags, self.rank, self.world, self._epoch,
+                                     nat.ptr(self._err, torch.int64), self.dev, st))
+        self._cur = nxt
+        return self._views[nxt]
+
+    def check(self):
+        e = int(self._err.item())
+        if e:
+            raise RuntimeError(f"fgk_peer_barrier: a peer never arrived at epoch {e}")
+
+    def matvec(self, x_full):
+        self.load(x_full)
+        return self.step().clone()
+
+    def diagonal(self):
+        if self._diag is None:
+            self._diag = allgather_vector(self.P.diagonal(), self.n)
+        return self._diag

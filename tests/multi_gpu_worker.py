@@ -44,10 +44,27 @@ def main():
     z = torch.complex(x, torch.flip(x, [0]))
     assert float((op.matvec(z) - Pfull.matvec(z)).abs().max()) < 1e-11
 
+    # fused H.v + all-gather over peer memory: same vectors, several ping-pong steps
+    fop = fd.FusedShardedOperator(Pblk)
+    yref = Pfull.matvec(x)
+    assert float((fop.matvec(x) - yref).abs().max()) < 1e-11
+    fop.load(x)
+    cur = x
+    for _ in range(5):
+        cur = Pfull.matvec(cur)
+        cur = cur / torch.linalg.norm(cur)
+        got = fop.step()
+        got /= torch.linalg.norm(got)          # in-place on the view: every rank scales its own copy
+        assert float((got - cur).abs().max()) < 1e-11
+    wf, _ = lowest_eigenpairs(fop, k=1, matvec=fop.matvec, diagonal=fop.diagonal(), dense_max=0)
+    fop.check()
+    fop.close()
+
     # Davidson and Taylor expm through the sharded operator
     w1, v1 = lowest_eigenpairs(Pfull, k=2, dense_max=0)
     w2, v2 = lowest_eigenpairs(op, k=2, matvec=op.matvec, diagonal=op.diagonal(), dense_max=0)
     assert float((w1 - w2).abs().max()) < 1e-9, (w1, w2)
+    assert abs(float(wf[0]) - float(w1[0])) < 1e-9
     psi = torch.zeros(n, dtype=torch.complex128, device=dev)
     psi[0] = 1.0
     e1 = expm_multiply(Pfull, psi, -0.1j)
