@@ -289,6 +289,12 @@ def run_ours(args):
     dets = torch.from_numpy(dets_np.view(np.int64)).to(dev)
 
     # ---- projected-H build (timed on the device, reported beside the headline) ----
+    # warm-up on a small slice of the same basis: loads the kernels and the torch scan /
+    # reduce modules (a fresh box pages them in from disk on first use)
+    warm = dets[:4096].contiguous()
+    Pw = H.projected_csr(warm, fgk.H_SYM, packed=True, sort_rows=True).to_sell()
+    Pw.matvec(torch.ones(warm.shape[0], dtype=torch.float64, device=dev))
+    del Pw, warm
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()

@@ -78,16 +78,22 @@ extern "C" int fgk_ham_create(const double* h1_host, const double* g_host, int n
     build_host_tables(h1_host, g_host, n_orb, T);
     fgk_ham* H = new fgk_ham();
     H->device = device;
+    // diagonal tables in ONE contiguous, 16-byte-granular buffer (a single TMA bulk copy
+    // stages it into shared memory): [h_pp padded to an even count][jks][jab]
+    const size_t npad = ((size_t)n_orb + 1) & ~(size_t)1, n2 = (size_t)n_orb * n_orb;
+    std::vector<double> dt(npad + 2 * n2, 0.0);
+    for (int p = 0; p < n_orb; p++) dt[p] = T.hdiag[p];
+    for (size_t i = 0; i < n2; i++) { dt[npad + i] = T.jks[i]; dt[npad + n2 + i] = T.jab[i]; }
     int rc;
     if ((rc = upload(T.h1, &H->h1)) || (rc = upload(T.g, &H->g)) || (rc = upload(T.w, &H->w)) ||
-        (rc = upload(T.hdiag, &H->hdiag)) || (rc = upload(T.jks, &H->jks)) ||
-        (rc = upload(T.jab, &H->jab))) {
+        (rc = upload(dt, &H->dtab))) {
         delete H;
         return rc;
     }
+    H->dtab_bytes = (unsigned)(dt.size() * sizeof(double));
     H->v.n_orb = n_orb; H->v.n_alpha = n_alpha; H->v.n_beta = n_beta; H->v.e_nuc = e_nuc;
     H->v.h1 = H->h1; H->v.g = H->g; H->v.w = H->w;
-    H->v.hdiag = H->hdiag; H->v.jks = H->jks; H->v.jab = H->jab;
+    H->v.hdiag = H->dtab; H->v.jks = H->dtab + npad; H->v.jab = H->dtab + npad + n2;
     *out = H;
     return FGK_OK;
 }
@@ -97,7 +103,7 @@ extern "C" int fgk_ham_destroy(fgk_ham_t h)
     if (!h) return FGK_OK;
     cudaSetDevice(h->device);
     cudaFree(h->h1); cudaFree(h->g); cudaFree(h->w);
-    cudaFree(h->hdiag); cudaFree(h->jks); cudaFree(h->jab);
+    cudaFree(h->dtab);
     delete h;
     return FGK_OK;
 }
@@ -187,21 +193,19 @@ extern "C" int fgk_unpack_i64(const uint64_t* dets, int64_t n, int n_orb, int64_
 }
 
 // ---- K2 diagonal -----------------------------------------------------------------------
-// one thread per determinant; h_pp / (J-K) / J tables staged in shared memory
-// (n*(2n+1) doubles: 37 KB at 48 orbitals, 66 KB at 64).
+// one thread per determinant; the h_pp / (J-K) / J tables (n*(2n+1) doubles: 37 KB at 48
+// orbitals, 66 KB at 64) are staged in shared memory by one TMA bulk copy per CTA.
 __global__ void __launch_bounds__(256)
-k_diag(HamView H, const fgk_det* __restrict__ dets, i64 n, double* __restrict__ out)
+k_diag(HamView H, unsigned tab_bytes, const fgk_det* __restrict__ dets, i64 n, double* __restrict__ out)
 {
-    extern __shared__ double s_tab[];
-    const int no = H.n_orb;
-    double* s_h = s_tab;
-    double* s_jks = s_tab + no;
-    double* s_jab = s_jks + no * no;
-    for (int i = threadIdx.x; i < no; i += blockDim.x) s_h[i] = H.hdiag[i];
-    for (int i = threadIdx.x; i < no * no; i += blockDim.x) { s_jks[i] = H.jks[i]; s_jab[i] = H.jab[i]; }
-    __syncthreads();
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    tma_stage_table(s_raw, H.hdiag, tab_bytes, &s_mbar);
+    const double* s_tab = reinterpret_cast<const double*>(s_raw);
     HamView S = H;
-    S.hdiag = s_h; S.jks = s_jks; S.jab = s_jab;
+    S.hdiag = s_tab;
+    S.jks = s_tab + (H.jks - H.hdiag);
+    S.jab = s_tab + (H.jab - H.hdiag);
     auto lds = [](const double* p) { return *p; };
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
         ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + j);
@@ -216,15 +220,14 @@ extern "C" int fgk_diag(fgk_ham_t h, const uint64_t* dets, int64_t n, double* ou
     if (n == 0) return FGK_OK;
     if (!dets || !out || n < 0) return fgk_fail(FGK_ERR_ARG, "fgk_diag: bad argument");
     FGK_CUDA(cudaSetDevice(h->device));
-    const int no = h->v.n_orb;
-    size_t smem = sizeof(double) * (size_t)(no + 2 * no * no);
+    size_t smem = h->dtab_bytes;
     static bool attr_set[64] = {false};
     if (smem > 48 * 1024 && !attr_set[h->device & 63]) {
         FGK_CUDA(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set[h->device & 63] = true;
     }
     k_diag<<<grid_for(n, 256, h->device, 4), 256, smem, (cudaStream_t)stream>>>(
-        h->v, (const fgk_det*)dets, n, out);
+        h->v, h->dtab_bytes, (const fgk_det*)dets, n, out);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }

@@ -36,7 +36,8 @@ struct fgk_ham {
     int device;
     HamView v;          // device pointers
     float *h1, *g, *w;
-    double *hdiag, *jks, *jab;
+    double* dtab;       // [h_pp (padded to even)] [jks n*n] [jab n*n], contiguous: one TMA bulk copy
+    unsigned dtab_bytes;
 };
 
 struct IndexView {
@@ -80,6 +81,39 @@ int fgk_sm_count(int device);
 
 // ---- device helpers ---------------------------------------------------------------
 #if defined(__CUDACC__)
+
+// ---- TMA (bulk async copy) staging of a contiguous table into shared memory -------------
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk
+// (global -> shared, completes on the mbarrier); every thread then waits on parity 0.
+// bytes: multiple of 16; both addresses 16-byte aligned.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_stage_table(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                                unsigned long long* mbar)
+{
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+    }
+    // all threads: wait for phase 0 to complete
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FGK_TMA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra FGK_TMA_DONE;\n"
+        "bra FGK_TMA_WAIT;\n"
+        "FGK_TMA_DONE:\n"
+        "}\n" :: "r"(smem_u32(mbar)) : "memory");
+}
 
 struct LdgF { __device__ __forceinline__ float operator()(const float* p) const { return __ldg(p); } };
 struct LdgD { __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); } };
