@@ -590,3 +590,43 @@ def test_config4_full_size_properties(fgk):
         assert len(rows) == per_row - 1
         col = P.cols[P.row_ptr[j]:P.row_ptr[j + 1]].cpu().numpy()     # row j of the symmetrised H
         assert np.array_equal(np.sort(np.append(rows, j)), col)
+
+
+def test_64_orbitals_on_device(fgk):
+    """n_orb = 64: both words fully used (bit 63, shift-by-64 hazards) through pack, diagonal,
+    connections, index and projected H."""
+    from oracle import oracle as orc
+    n_orb, na, nb = 64, 2, 1
+    rng = np.random.default_rng(64)
+    h1 = rng.standard_normal((n_orb, n_orb)); h1 = 0.5 * (h1 + h1.T)
+    g = np.zeros((n_orb,) * 4)
+    idx = rng.integers(0, n_orb, size=(40000, 4))
+    vals = rng.standard_normal(40000) * 0.1
+    for perm in ((0, 1, 2, 3), (1, 0, 2, 3), (0, 1, 3, 2), (1, 0, 3, 2), (2, 3, 0, 1), (3, 2, 0, 1), (2, 3, 1, 0), (3, 2, 1, 0)):
+        g[idx[:, perm[0]], idx[:, perm[1]], idx[:, perm[2]], idx[:, perm[3]]] = vals
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, g, 0.25, na + nb, n_orb, na, nb), "cuda:0")
+    O = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), na, nb, 0.25)
+    dets = np.zeros((4, 2 * n_orb), np.uint8)
+    dets[0, [0, 1]] = 1; dets[0, n_orb + 0] = 1
+    dets[1, [62, 63]] = 1; dets[1, n_orb + 63] = 1
+    dets[2, [0, 63]] = 1; dets[2, n_orb + 31] = 1
+    dets[3, [17, 40]] = 1; dets[3, n_orb + 5] = 1
+    d = H.pack(t64(dets))
+    assert np.array_equal(dets_np(d), pack_np(dets, n_orb))
+    assert np.array_equal(H.unpack(d).cpu().numpy(), dets.astype(np.int64))
+    assert np.abs(H.diagonal_elements_batch(t64(dets)).cpu().numpy() - O.diag(dets)).max() < TOL
+    c, e, src = H.get_connections_batch(t64(dets))
+    oc, oe, osrc, _ = O.connections_batch(dets)
+    assert np.array_equal(c.cpu().numpy().astype(np.uint8), oc)
+    assert np.array_equal(e.cpu().numpy().view(np.uint32), oe.view(np.uint32))
+    assert np.array_equal(src.cpu().numpy(), osrc)
+    # a basis made of det 0 and its first 300 connections: sorted union + projected H
+    basis = np.unique(np.concatenate([dets, oc[:300]]), axis=0)
+    srt = fgk.sort_unique_dets(H.pack(t64(np.concatenate([dets, oc[:300], dets]))), n_orb)
+    assert np.array_equal(unpack_np(dets_np(srt), n_orb), basis)
+    D = O.dense_H(basis)
+    for mode, ref in ((fgk.H_RAW, D), (fgk.H_SYM, 0.5 * (D + D.T))):
+        A = H.projected_csr(t64(basis), mode).to_scipy().toarray()
+        off = ~np.eye(len(basis), dtype=bool)
+        assert np.array_equal(A[off], ref[off])
+        assert np.abs(np.diag(A) - np.diag(ref)).max() < TOL

@@ -123,3 +123,37 @@ def test_structured_bra_rows_equal_flat_enumeration(name, mode, scan):
         assert np.array_equal(c1[:m1][o1], c2[:m2][o2])
         assert np.array_equal(v1[:m1][o1], v2[:m2][o2])
     hostcheck().hc_ham_destroy(hc)
+
+
+def test_64_orbitals_bit63_edges():
+    """n_orb = 64 uses every bit of both words (shift-by-64 hazards, sign bit)."""
+    from helpers import synth_integrals
+    n_orb, na, nb = 64, 2, 1
+    rng = np.random.default_rng(64)
+    h1 = rng.standard_normal((n_orb, n_orb)); h1 = 0.5 * (h1 + h1.T)
+    g = np.zeros((n_orb,) * 4)
+    idx = rng.integers(0, n_orb, size=(40000, 4))
+    vals = rng.standard_normal(40000) * 0.1
+    for perm in ((0, 1, 2, 3), (1, 0, 2, 3), (0, 1, 3, 2), (1, 0, 3, 2), (2, 3, 0, 1), (3, 2, 0, 1), (2, 3, 1, 0), (3, 2, 1, 0)):
+        g[idx[:, perm[0]], idx[:, perm[1]], idx[:, perm[2]], idx[:, perm[3]]] = vals
+    hc = hostcheck().hc_ham_create(_p(np.ascontiguousarray(h1)), _p(g), n_orb, na, nb, 0.25)
+    H = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), na, nb, 0.25)
+    dets = np.zeros((4, 2 * n_orb), np.uint8)
+    dets[0, [0, 1]] = 1; dets[0, n_orb + 0] = 1            # lowest orbitals (highest bits)
+    dets[1, [62, 63]] = 1; dets[1, n_orb + 63] = 1         # highest orbitals (bit 0)
+    dets[2, [0, 63]] = 1; dets[2, n_orb + 31] = 1
+    dets[3, [17, 40]] = 1; dets[3, n_orb + 5] = 1
+    pk = pack_np(dets, n_orb)
+    assert np.array_equal(unpack_np(pk, n_orb), dets)
+    out = np.zeros(4)
+    hostcheck().hc_diag(hc, _p(pk), 4, _p(out))
+    assert np.abs(out - H.diag(dets)).max() < 1e-9
+    for j in range(4):
+        oc, oe = H.connections(dets[j])
+        cap = len(oc) + 8
+        od, el = np.zeros((cap, 2), np.uint64), np.zeros(cap, np.float32)
+        m = hostcheck().hc_connections(hc, int(pk[j, 0]), int(pk[j, 1]), _p(od), _p(el), cap)
+        assert m == len(oc)
+        assert np.array_equal(unpack_np(od[:m], n_orb), oc)
+        assert np.array_equal(el[:m].view(np.uint32), oe.view(np.uint32))
+    hostcheck().hc_ham_destroy(hc)
