@@ -55,6 +55,7 @@ _SIGNATURES = {
     "fgk_pt2_accumulate": (ci, [vp, vp, vp, vp, vp, i64, ci, ci, ci, vp]),
     "fgk_pt2_merge": (ci, [vp, vp, vp, i64, ci, vp]),
     "fgk_pt2_count": (ci, [vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(ci)]),
+    "fgk_partition_by_owner": (ci, [vp, vp, i64, ci, vp, vp, vp, ci, ci, vp]),
     "fgk_pt2_export": (ci, [vp, vp, i64, dbl, vp, vp, vp, vp, C.POINTER(i64), vp]),
 }
 

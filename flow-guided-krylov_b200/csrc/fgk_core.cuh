@@ -362,3 +362,70 @@ FGK_HD void double_from_strings(u64 from, u64 to, int n, int& h0, int& h1, int& 
     e0 = n - 1 - (63 - fgk_clz(es));
     e1 = n - 1 - fgk_ctz(es);
 }
+
+// ---- split element evaluation: table value and sign parity separately ------------------------
+// (the count pass of the projected-H builder only needs |value| > 1e-12; the fill pass adds
+// the sign).  The fast parities use c_q = c_s = 1 (the holes ARE occupied in the ket) and the
+// fixed site order of each class; fgk_hostcheck verifies them against sign2_parity.
+template <class Ld>
+FGK_HD float exc_value_ket(const HamView& H, const Excitation& x, Ld ldf)
+{
+    const int n = H.n_orb;
+    if (x.cls < 2) return ldf(H.h1 + (size_t)x.e0 * n + x.h0);
+    return ldf((x.cls == 4 ? H.g : H.w) + idx4(n, x.e0, x.h0, x.e1, x.h1));
+}
+
+template <class Ld>
+FGK_HD float exc_value_bra(const HamView& H, const Excitation& x, Ld ldf)
+{
+    const int n = H.n_orb;
+    if (x.cls < 2) return ldf(H.h1 + (size_t)x.h0 * n + x.e0);
+    return ldf((x.cls == 4 ? H.g : H.w) + idx4(n, x.h0, x.e0, x.h1, x.e1));
+}
+
+// orbitals o with min(x,y) <= o < max(x,y)
+FGK_HD u64 span_mask(int n, int x, int y) { return below_mask(n, x) ^ below_mask(n, y); }
+
+// parity of the reference sign for the connection ket -> ket + x (x's holes q=h0,s=h1 occupied
+// and particles p=e0,r=e1 empty in `ket`)
+FGK_HD int exc_parity_ket(fgk_det ket, int n, const Excitation& x)
+{
+    const int q = x.h0, s = x.h1, p = x.e0, r = x.e1;
+    switch (x.cls) {
+    case 0: return sign1_parity(ket.a, n, p, q);
+    case 1: return sign1_parity(ket.b, n, p, q);
+    case 2:
+    case 3: {
+        const u64 w = x.cls == 2 ? ket.a : ket.b;
+        int t = fgk_popc(w & (span_mask(n, p, q) ^ span_mask(n, r, s)));
+        t += (p < s) + (r < s) + (p < q) + (r < q) + (q < r) + 1;     // -[q<r] - 1  ==  +[q<r] + 1 (mod 2)
+        return t & 1;
+    }
+    default: {
+        int t = fgk_popc(ket.a & span_mask(n, p, q)) + fgk_popc(ket.b & span_mask(n, r, s));
+        t += (r < s) + (p < q) + 1;
+        return t & 1;
+    }
+    }
+}
+
+// <D|H|D+x> as get_connections(D+x) reports it: roles reversed on the ket D+x
+FGK_HD int exc_parity_bra(fgk_det bra, int n, const Excitation& x)
+{
+    fgk_det ket = apply_excitation(bra, n, x);
+    Excitation rx;
+    rx.cls = x.cls; rx.h0 = x.e0; rx.h1 = x.e1; rx.e0 = x.h0; rx.e1 = x.h1;
+    return exc_parity_ket(ket, n, rx);
+}
+
+// ket_element / bra_element with the split, class-specialised evaluation (bit-identical
+// results; verified against the generic forms by fgk_hostcheck's hc_check_split)
+template <class Ld>
+FGK_HD bool ket_element_fast(const HamView& H, fgk_det ket, const Excitation& x, Ld ldf, float& out)
+{
+    float v = exc_value_ket(H, x, ldf);
+    float av = v < 0.f ? -v : v;
+    if (!(av > 1e-12f)) return false;
+    out = exc_parity_ket(ket, H.n_orb, x) ? -v : v;
+    return true;
+}

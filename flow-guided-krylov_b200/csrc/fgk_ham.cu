@@ -269,9 +269,9 @@ k_conn(HamView H, const fgk_det* __restrict__ dets, i64 n, i64* __restrict__ cou
                 x.h0 = q; x.e0 = p; x.h1 = 0; x.e1 = 0;
                 float ea = 0.f, eb = 0.f;
                 x.cls = 0;
-                bool ka = va && ket_element(H, d, x, ldf, ea);
+                bool ka = va && ket_element_fast(H, d, x, ldf, ea);
                 x.cls = 1;
-                bool kb = vb && ket_element(H, d, x, ldf, eb);
+                bool kb = vb && ket_element_fast(H, d, x, ldf, eb);
                 unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
                 if (FILL) {
                     i64 o = pos + __popc(ba & lt) + __popc(bb & lt);
@@ -282,7 +282,7 @@ k_conn(HamView H, const fgk_det* __restrict__ dets, i64 n, i64* __restrict__ cou
             },
             [&](bool valid, const Excitation& x) {
                 float e = 0.f;
-                bool k = valid && ket_element(H, d, x, ldf, e);
+                bool k = valid && ket_element_fast(H, d, x, ldf, e);
                 unsigned b = __ballot_sync(0xffffffffu, k);
                 if (FILL && k) put(pos + __popc(b & lt), x, e);
                 pos += __popc(b);

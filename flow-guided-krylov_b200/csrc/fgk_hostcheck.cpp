@@ -200,4 +200,43 @@ long hc_bra_row2(void* h, const u64* basis, long n, long i, int mode, int scan, 
     return m;
 }
 
+// fast split evaluation (exc_value_* / exc_parity_*) against the generic element functions,
+// over every excitation of the given determinants; returns the number of mismatches
+long hc_check_split(void* h, const u64* dets, long n_dets)
+{
+    HcHam* H = (HcHam*)h;
+    long bad = 0;
+    for (long i = 0; i < n_dets; i++) {
+        uint8_t buf[256];
+        DetCtx c;
+        fgk_det d = {dets[2 * i], dets[2 * i + 1]};
+        detctx_fill_host(c, H->V.n_orb, d, buf);
+        auto chk = [&](const Excitation& x) {
+            float vk = 0.f, vb = 0.f;
+            bool kk = ket_element(H->V, d, x, ldf_host, vk);
+            bool kb = bra_element(H->V, d, x, ldf_host, vb);
+            float rk = exc_value_ket(H->V, x, ldf_host), rb = exc_value_bra(H->V, x, ldf_host);
+            bool fk = (rk < 0 ? -rk : rk) > 1e-12f, fb = (rb < 0 ? -rb : rb) > 1e-12f;
+            if (fk != kk || fb != kb) { bad++; return; }
+            if (kk && (exc_parity_ket(d, c.n, x) ? -rk : rk) != vk) bad++;
+            if (kb && (exc_parity_bra(d, c.n, x) ? -rb : rb) != vb) bad++;
+        };
+        for (int t = 0; t < c.n_s; t++) {
+            int p, q; bool va, vb;
+            decode_single(c, t, p, q, va, vb);
+            Excitation x; x.h1 = x.e1 = 0; x.h0 = q; x.e0 = p;
+            if (va) { x.cls = 0; chk(x); }
+            if (vb) { x.cls = 1; chk(x); }
+        }
+        const int sizes[3] = {c.n_aa, c.n_bb, c.n_ab};
+        for (int st = 2; st <= 4; st++)
+            for (int t = 0; t < sizes[st - 2]; t++) {
+                Excitation x;
+                decode_double(c, st, t, x);
+                chk(x);
+            }
+    }
+    return bad;
+}
+
 }  // extern "C"

@@ -124,7 +124,8 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
             vals[pos] = diag_element(H, d, ldd);
         }
         pos += 1;
-        // full-key probe + element of one candidate per lane; rank inside the row by ballot
+        // full-key probe + element of one candidate per lane; rank inside the row by ballot.
+        // The count pass needs only |value| > 1e-12 (no signs) unless exact zeros are dropped.
         auto emit = [&](bool valid, const Excitation& x) {
             int j = -1;
             double v = 0.0;
@@ -133,13 +134,20 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
                 fgk_det o = apply_excitation(d, n, x);
                 j = index_find(I, o);
                 if (j >= 0) {
-                    float vij = 0.f, vji = 0.f;
-                    bool kij = bra_element(H, d, x, ldf, vij);
-                    bool kji = sym ? ket_element(H, d, x, ldf, vji) : false;
+                    const float rb = exc_value_bra(H, x, ldf);
+                    const bool kij = fabsf(rb) > 1e-12f;
+                    float rk = 0.f;
+                    bool kji = false;
+                    if (sym) { rk = exc_value_ket(H, x, ldf); kji = fabsf(rk) > 1e-12f; }
                     keep = kij || kji;
-                    v = sym ? 0.5 * ((double)(kij ? vij : 0.f) + (double)(kji ? vji : 0.f))
-                            : (double)vij;
-                    if (drop0 && v == 0.0) keep = false;
+                    if (keep && (FILL || drop0)) {
+                        Excitation rx;
+                        rx.cls = x.cls; rx.h0 = x.e0; rx.h1 = x.e1; rx.e0 = x.h0; rx.e1 = x.h1;
+                        const float vij = kij ? (exc_parity_ket(o, n, rx) ? -rb : rb) : 0.f;   // <i|H|j>, ket j = o
+                        const float vji = kji ? (exc_parity_ket(d, n, x) ? -rk : rk) : 0.f;    // <j|H|i>, ket i = d
+                        v = sym ? 0.5 * ((double)vij + (double)vji) : (double)vij;
+                        if (drop0 && v == 0.0) keep = false;
+                    }
                 }
             }
             unsigned b = __ballot_sync(0xffffffffu, keep);

@@ -113,7 +113,7 @@ k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_
         auto visit = [&](bool valid, const Excitation& x) {
             if (!valid) return;
             float el;
-            if (!ket_element(H, d, x, ldf, el)) return;          // reference filter
+            if (!ket_element_fast(H, d, x, ldf, el)) return;          // reference filter
             fgk_det o = apply_excitation(d, c.n, x);
             const u64 h = det_hash(o.a, o.b);
             if (n_pass > 1 && (unsigned)((h >> 40) % n_pass) != pass_id) return;
@@ -318,5 +318,61 @@ extern "C" int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double
     FGK_CUDA(cudaMemcpyAsync(&live, ws->v.counters + 3, sizeof(live), cudaMemcpyDeviceToHost, st));
     FGK_CUDA(cudaStreamSynchronize(st));
     if (n_live) *n_live = (int64_t)live;
+    return FGK_OK;
+}
+
+// ---- dedup exchange: partition (determinant, value) pairs by owner rank ----------------------
+// owner = (hash >> 24) % world (bits disjoint from the bucket-pass bits).  Count, then scatter
+// into contiguous per-owner segments with warp-aggregated cursor claims; the segments are the
+// send buffers of the all-to-all (dist.exchange_by_owner).
+__device__ __forceinline__ int owner_of_det(u64 a, u64 b, int world)
+{
+    return (int)(((det_hash(a, b) >> 24) & 0xffffull) % (unsigned)world);
+}
+
+__global__ void __launch_bounds__(256)
+k_partition(const fgk_det* __restrict__ dets, const double* __restrict__ vals, i64 m, int world,
+            unsigned long long* cursors, fgk_det* __restrict__ out_dets, double* __restrict__ out_vals,
+            bool scatter)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 rounds = (m + stride - 1) / stride;
+    for (i64 it = 0; it < rounds; it++) {
+        const i64 i = it * stride + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = i < m;
+        ulonglong2 d = make_ulonglong2(0, 0);
+        int own = -1 - lane;                       // distinct dummy keys for idle lanes
+        if (live) {
+            d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + i);
+            own = owner_of_det(d.x, d.y, world);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, own);
+        if (!live) continue;
+        const int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(cursors + own, (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        if (scatter) {
+            const i64 o = (i64)base + __popc(peers & ((1u << lane) - 1u));
+            reinterpret_cast<ulonglong2*>(out_dets)[o] = d;
+            out_vals[o] = __ldg(vals + i);
+        }
+    }
+}
+
+extern "C" int fgk_partition_by_owner(const uint64_t* dets, const double* vals, int64_t m, int world,
+                                      uint64_t* cursors, uint64_t* out_dets, double* out_vals,
+                                      int scatter, int device, void* stream)
+{
+    if (m == 0) return FGK_OK;
+    if (!dets || !cursors || m < 0 || world < 1 || (scatter && (!vals || !out_dets || !out_vals)))
+        return fgk_fail(FGK_ERR_ARG, "fgk_partition_by_owner: bad argument");
+    FGK_CUDA(cudaSetDevice(device));
+    i64 need = (m + 255) / 256, cap = (i64)fgk_sm_count(device) * 8;
+    k_partition<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        (const fgk_det*)dets, vals, m, world, (unsigned long long*)cursors, (fgk_det*)out_dets, out_vals,
+        scatter != 0);
+    FGK_LAUNCH_CHECK();
     return FGK_OK;
 }

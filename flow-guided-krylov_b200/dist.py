@@ -92,10 +92,26 @@ def exchange_by_owner(dets: torch.Tensor, vals: torch.Tensor, group=None):
     rank, ws = world()
     if ws == 1:
         return dets, vals
-    own = owner_of(dets, ws)
-    order = torch.argsort(own, stable=True)
-    dets, vals, own = dets[order].contiguous(), vals[order].contiguous(), own[order]
-    send_counts = torch.bincount(own, minlength=ws).to(torch.int64)
+    if dets.is_cuda:
+        # count + scatter kernels (fgk_partition_by_owner) instead of a 64-bit sort
+        from . import _native as nat
+        L, dev_i, st = nat.lib(), nat.device_index(dets.device), nat.stream_ptr(dets.device)
+        dets, vals = dets.contiguous(), vals.to(torch.float64).contiguous()
+        m = dets.shape[0]
+        send_counts = torch.zeros(ws, dtype=torch.int64, device=dets.device)
+        nat.check(L.fgk_partition_by_owner(nat.ptr(dets), None, m, ws, nat.ptr(send_counts), None, None,
+                                           0, dev_i, st))
+        cursors = torch.zeros(ws, dtype=torch.int64, device=dets.device)
+        torch.cumsum(send_counts[:-1], 0, out=cursors[1:])
+        sd, sv = torch.empty_like(dets), torch.empty_like(vals)
+        nat.check(L.fgk_partition_by_owner(nat.ptr(dets), nat.ptr(vals), m, ws, nat.ptr(cursors),
+                                           nat.ptr(sd), nat.ptr(sv), 1, dev_i, st))
+        dets, vals = sd, sv
+    else:
+        own = owner_of(dets, ws)
+        order = torch.argsort(own, stable=True)
+        dets, vals, own = dets[order].contiguous(), vals[order].contiguous(), own[order]
+        send_counts = torch.bincount(own, minlength=ws).to(torch.int64)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     sc, rc = send_counts.tolist(), recv_counts.tolist()

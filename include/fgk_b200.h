@@ -208,6 +208,14 @@ int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy, ui
                    double* out_coupling, double* out_diag, double* out_importance,
                    int64_t* n_live, void* stream);
 
+/* Dedup exchange helper: owner rank of a determinant = (hash >> 24) % world.
+ * scatter = 0: cursors[w] += number of pairs owned by w (cursors zeroed by the caller);
+ * scatter = 1: cursors[w] hold the segment starts (exclusive scan of the counts); pairs are
+ * copied into out_dets / out_vals so that every owner's pairs are contiguous. */
+int fgk_partition_by_owner(const uint64_t* dets, const double* vals, int64_t m, int world,
+                           uint64_t* cursors, uint64_t* out_dets, double* out_vals, int scatter,
+                           int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

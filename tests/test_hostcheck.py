@@ -157,3 +157,13 @@ def test_64_orbitals_bit63_edges():
         assert np.array_equal(unpack_np(od[:m], n_orb), oc)
         assert np.array_equal(el[:m].view(np.uint32), oe.view(np.uint32))
     hostcheck().hc_ham_destroy(hc)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_split_value_and_fast_parity_equal_generic_elements(name):
+    g = load_golden("ham_" + name)
+    hc, _, n_orb = make(g)
+    dets = np.concatenate([g["dets"], g["basis"]])
+    pk = pack_np(dets, n_orb)
+    assert hostcheck().hc_check_split(hc, _p(pk), len(pk)) == 0
+    hostcheck().hc_ham_destroy(hc)
