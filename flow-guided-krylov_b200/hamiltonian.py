@@ -130,6 +130,29 @@ class ProjectedH:
             dev, nat.stream_ptr(self.device)))
         return y
 
+    def matvec_host(self, x_host, out=None):
+        """Host-buffer form of matvec: x_host (CPU tensor or numpy array, ideally pinned) is
+        copied to the device, y = H x is computed, and y comes back in a CPU tensor (pinned,
+        reused between calls unless `out` is given).  The call returns when y is complete."""
+        if not torch.is_tensor(x_host):
+            x_host = torch.from_numpy(np.ascontiguousarray(x_host))
+        dev = self.cols.device if self.cols.numel() else self._sell[1].device
+        key = (x_host.dtype, x_host.shape[0])
+        buf = getattr(self, "_host_io", None)
+        if buf is None or buf[0] != key:
+            ydt = torch.complex128 if x_host.is_complex() else torch.float64
+            buf = (key, torch.empty(self.n, dtype=ydt, device=dev),
+                   torch.empty(self.n_rows, dtype=ydt, device=dev),
+                   torch.empty(self.n_rows, dtype=ydt).pin_memory())
+            self._host_io = buf
+        _, xd, yd, yh = buf
+        xd.copy_(x_host, non_blocking=True)
+        self.matvec(xd, out=yd)
+        dst = out if out is not None else yh
+        dst.copy_(yd, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return dst
+
     def diagonal(self):
         """the diagonal is the first entry of every row until sort_rows()."""
         if getattr(self, "_diag_cache", None) is not None:

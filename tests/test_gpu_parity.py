@@ -630,3 +630,46 @@ def test_64_orbitals_on_device(fgk):
         off = ~np.eye(len(basis), dtype=bool)
         assert np.array_equal(A[off], ref[off])
         assert np.abs(np.diag(A) - np.diag(ref)).max() < TOL
+
+
+def test_concurrent_get_connections_threads(fgk):
+    """the reference calls get_connections from an 8-thread pool (molecular.py:537-565);
+    handles are immutable, so concurrent host threads must get the single-thread answers."""
+    from concurrent.futures import ThreadPoolExecutor
+    g = load_golden("ham_n2")
+    H, _, _ = make_pair(fgk, g)
+    offs = g["conn_offsets"]
+    dets = [t64(d) for d in g["dets"]]
+
+    def work(j):
+        c, e = H.get_connections(dets[j])
+        return j, c.cpu().numpy().astype(np.uint8), e.cpu().numpy()
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        results = list(ex.map(work, list(range(len(dets))) * 6))
+    for j, c, e in results:
+        assert np.array_equal(c, g["conn_cfgs"][offs[j]:offs[j + 1]])
+        assert np.array_equal(e.view(np.uint32), g["conn_elems"][offs[j]:offs[j + 1]].view(np.uint32))
+
+
+def test_error_conventions(fgk):
+    from flow_guided_krylov_b200 import _native as nat
+    g = load_golden("ham_lih")
+    H, _, _ = make_pair(fgk, g)
+    with pytest.raises(ValueError):
+        H.pack(torch.zeros(3, 7, dtype=torch.long))                  # wrong number of sites
+    with pytest.raises(RuntimeError):
+        nat.ptr(torch.zeros(4))                                      # CPU tensor at the C boundary
+    with pytest.raises(RuntimeError, match="n_orb"):
+        fgk.MolecularHamiltonian(fgk.MolecularIntegrals(np.eye(65), np.zeros((65,) * 4), 0.0, 2, 65, 1, 1), "cuda:0")
+    P = H.projected_csr(t64(g["basis"]), fgk.H_RAW)
+    with pytest.raises(ValueError):
+        P.matvec(torch.zeros(3, dtype=torch.float64, device="cuda"))
+    # host-buffer API == device API
+    x = np.random.default_rng(0).standard_normal(P.n)
+    y = P.matvec(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(P.matvec_host(torch.from_numpy(x).pin_memory()).numpy(), y)
+    assert np.array_equal(P.matvec_host(x).numpy(), y)
+    z = x + 1j * x[::-1]
+    yz = P.matvec(torch.from_numpy(z).cuda()).cpu().numpy()
+    assert np.array_equal(P.matvec_host(torch.from_numpy(z)).numpy(), yz)
