@@ -37,6 +37,7 @@ _SIGNATURES = {
     "fgk_index_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "fgk_projh_count": (ci, [vp, vp, i64, i64, ci, vp, vp]),
     "fgk_projh_fill": (ci, [vp, vp, i64, i64, ci, vp, vp, vp, vp]),
+    "fgk_projh_fill_sell": (ci, [vp, vp, i64, i64, ci, vp, vp, vp, vp]),
     "fgk_csr_sort_rows": (ci, [i64, vp, vp, vp, ci, vp]),
     "fgk_spmv_f64": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_z": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),

@@ -100,8 +100,8 @@ static const int SINGLE_LIST_CAP = 1024;   // n_occ * n_virt <= 32 * 32
 template <bool FILL>
 __global__ void __launch_bounds__(FGK_BLOCK)
 k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int mode,
-         i64* __restrict__ counts, const i64* __restrict__ row_ptr, int32_t* __restrict__ cols,
-         double* __restrict__ vals)
+         i64* __restrict__ counts, const i64* __restrict__ row_ptr, const i64* __restrict__ slice_ptr,
+         int32_t* __restrict__ cols, double* __restrict__ vals)
 {
     __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
     __shared__ unsigned short s_single[FGK_WARPS_PER_BLOCK][2][SINGLE_LIST_CAP];
@@ -118,10 +118,18 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
         fgk_det d = {dv.x, dv.y};
         DetCtx c;
         warp_build_ctx(c, n, d, s_lists[wib], lane);
-        i64 pos = FILL ? row_ptr[i - row_begin] : 0;
+        // pos = index of the next entry INSIDE the row; at(k) = where entry k of this row lives:
+        // CSR (row_ptr) or directly SELL-32 (slice_ptr: lane-interleaved pairs, see fgk_spmv.cu)
+        const i64 rl = i - row_begin;
+        const i64 row_base = !FILL ? 0 : (slice_ptr ? __ldg(slice_ptr + (rl >> 5)) + 2 * (rl & 31)
+                                                    : __ldg(row_ptr + rl));
+        auto at = [&](i64 k) -> i64 {
+            return slice_ptr ? row_base + (k >> 1) * 64 + (k & 1) : row_base + k;
+        };
+        i64 pos = 0;
         if (FILL && lane == 0) {
-            cols[pos] = (int32_t)i;
-            vals[pos] = diag_element(H, d, ldd);
+            cols[at(0)] = (int32_t)i;
+            vals[at(0)] = diag_element(H, d, ldd);
         }
         pos += 1;
         // full-key probe + element of one candidate per lane; rank inside the row by ballot.
@@ -152,7 +160,7 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
             }
             unsigned b = __ballot_sync(0xffffffffu, keep);
             if (FILL && keep) {
-                i64 o = pos + __popc(b & lt);
+                const i64 o = at(pos + __popc(b & lt));
                 cols[o] = j;
                 vals[o] = v;
             }
@@ -290,7 +298,7 @@ extern "C" int fgk_projh_count(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, 
     else
         k_projh2<false><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
             h->v, idx->v, proj_lists(h, idx), row_begin, row_end, mode, (i64*)counts, nullptr, nullptr,
-            nullptr);
+            nullptr, nullptr);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }
@@ -312,7 +320,28 @@ extern "C" int fgk_projh_fill(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, i
     else
         k_projh2<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
             h->v, idx->v, proj_lists(h, idx), row_begin, row_end, mode, nullptr, (const i64*)row_ptr,
-            cols, vals);
+            nullptr, cols, vals);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+// fill rows straight into SELL-32 storage (no CSR copy): slice_ptr as for fgk_sell_fill; the
+// arrays must be zero-filled by the caller (padding entries stay value 0 / column 0)
+extern "C" int fgk_projh_fill_sell(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end,
+                                   int mode, const int64_t* slice_ptr, int32_t* sell_cols,
+                                   double* sell_vals, void* stream)
+{
+    if (!h || !idx) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill_sell: null handle");
+    if (row_begin < 0 || row_end > idx->v.n || row_begin > row_end)
+        return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill_sell: bad row range");
+    if (row_begin == row_end) return FGK_OK;
+    if (!slice_ptr || !sell_cols || !sell_vals) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill_sell: null pointer");
+    if (mode & FGK_H_FLAT_WALK) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_projh_fill_sell: not with FLAT_WALK");
+    if (h->device != idx->device) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill_sell: device mismatch");
+    FGK_CUDA(cudaSetDevice(h->device));
+    k_projh2<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+        h->v, idx->v, proj_lists(h, idx), row_begin, row_end, mode, nullptr, nullptr,
+        (const i64*)slice_ptr, sell_cols, sell_vals);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }

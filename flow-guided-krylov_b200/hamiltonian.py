@@ -55,7 +55,13 @@ class ProjectedH:
     def nnz(self):
         return int(getattr(self, "_nnz", None) or self.vals.numel())
 
+    def _need_csr(self, what):
+        if getattr(self, "sell_only", False):
+            raise RuntimeError(f"{what} needs the CSR arrays; this operator was built SELL-only "
+                               "(use projected_csr instead of projected_sell)")
+
     def sort_rows(self):
+        self._need_csr("sort_rows")
         if not self.sorted_rows and self.nnz:
             nat.check(nat.lib().fgk_csr_sort_rows(
                 self.n_rows, nat.ptr(self.row_ptr, torch.int64), nat.ptr(self.cols, torch.int32),
@@ -166,6 +172,7 @@ class ProjectedH:
         return self.vals[self.row_ptr[:-1]]
 
     def to_dense(self):
+        self._need_csr("to_dense")
         rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.cols.device),
                                        self.row_ptr[1:] - self.row_ptr[:-1])
         D = torch.zeros(self.n_rows, self.n, dtype=torch.float64, device=self.cols.device)
@@ -408,6 +415,50 @@ class MolecularHamiltonian:
             P.build_profile = {"count_ms": ev[0].elapsed_time(ev[1]), "fill_ms": ev[2].elapsed_time(ev[3]),
                                "alloc_ms": 1e3 * t_alloc}
         return P.sort_rows() if sort_rows else P
+
+    def projected_sell(self, basis, mode=nat.H_SYM, row_begin=0, row_end=None,
+                       index: Optional[BasisIndex] = None, packed=False) -> ProjectedH:
+        """Rows [row_begin,row_end) of the projected H built STRAIGHT into SELL-32 storage
+        (count -> slice widths -> fgk_projh_fill_sell): the operator for Krylov work, at half the
+        peak memory of projected_csr(...).to_sell() -- but the lane-interleaved layout makes the
+        fill a strided write (measured 2.5x slower than CSR fill + conversion on config 4), so use it
+        when memory, not build time, is the limit.  matvec / diagonal / nnz work; the CSR-only
+        views (to_dense, to_scipy, sort_rows) are not available on it."""
+        dets = basis if packed else self.pack(basis)
+        idx = index if index is not None else BasisIndex(dets)
+        n = len(idx)
+        row_end = n if row_end is None else row_end
+        rows = row_end - row_begin
+        st = nat.stream_ptr(self.device)
+        counts = torch.empty(rows, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().fgk_projh_count(self._h, idx._h, row_begin, row_end, mode,
+                                            nat.ptr(counts, torch.int64), st))
+        row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=row_ptr[1:])
+        n_slices = (rows + 31) // 32
+        lens = torch.zeros(n_slices * 32, dtype=torch.int64, device=self.device)
+        lens[:rows] = counts
+        width = (lens.view(n_slices, 32).max(dim=1).values + 1) // 2 * 2
+        slice_ptr = torch.zeros(n_slices + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(width * 32, 0, out=slice_ptr[1:])
+        total = int(slice_ptr[-1].item()) if n_slices else 0
+        sc = torch.zeros(total, dtype=torch.int32, device=self.device)
+        sv = torch.zeros(total, dtype=torch.float64, device=self.device)
+        if total:
+            nat.check(nat.lib().fgk_projh_fill_sell(
+                self._h, idx._h, row_begin, row_end, mode, nat.ptr(slice_ptr, torch.int64),
+                nat.ptr(sc, torch.int32), nat.ptr(sv, torch.float64), st))
+        empty_c = torch.empty(0, dtype=torch.int32, device=self.device)
+        empty_v = torch.empty(0, dtype=torch.float64, device=self.device)
+        P = ProjectedH(n, row_ptr, empty_c, empty_v, self.device, row_begin, row_end, mode)
+        P._index = idx
+        P._sell = (slice_ptr, sc, sv)
+        P._nnz = int(row_ptr[-1].item()) if rows else 0
+        # the diagonal is entry 0 of every row: slice base + 2 * lane
+        r = torch.arange(rows, device=self.device)
+        P._diag_cache = sv[slice_ptr[r // 32] + 2 * (r % 32)] if rows else empty_v
+        P.sell_only = True
+        return P
 
     @torch.no_grad()
     def matrix_elements_fast(self, configs: torch.Tensor) -> torch.Tensor:

@@ -127,6 +127,11 @@ int fgk_projh_fill(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_
                    const int64_t* row_ptr, int32_t* cols, double* vals, void* stream);
 int fgk_csr_sort_rows(int64_t n_rows, const int64_t* row_ptr, int32_t* cols, double* vals,
                       int device, void* stream);
+/* Same fill, but straight into SELL-32 storage (layout under K6 below; no CSR copy is made):
+ * slice_ptr from the row counts as for fgk_sell_fill; sell_cols / sell_vals must be
+ * zero-filled by the caller. */
+int fgk_projh_fill_sell(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end, int mode,
+                        const int64_t* slice_ptr, int32_t* sell_cols, double* sell_vals, void* stream);
 
 /* ---- K6 sparse H.v, FP64 CSR ----------------------------------------------------------
  * replaces scipy's csr_matvec inside eigsh (skqd.py:784, residual_expansion.py:435,

@@ -470,6 +470,16 @@ def test_large_cas_window_properties(fgk):
     ycsr = P.matvec(x)
     P.to_sell()
     assert float((P.matvec(x) - ycsr).abs().max()) < 1e-10
+    # SELL-32 built directly by the fill kernel (no CSR): same operator, diagonal and size
+    Q = H.projected_sell(dets, fgk.H_RAW, packed=True, index=P._index)
+    assert Q.nnz == P.nnz and torch.equal(Q.row_ptr, P.row_ptr)
+    assert float((Q.matvec(x) - ycsr).abs().max()) < 1e-10
+    assert torch.equal(Q.diagonal(), P.diagonal())
+    Qb = H.projected_sell(dets, fgk.H_RAW, packed=True, index=P._index, row_begin=1000, row_end=n - 333)
+    assert float((Qb.matvec(x) - ycsr[1000:n - 333]).abs().max()) < 1e-10
+    with pytest.raises(RuntimeError):
+        Q.to_dense()
+    del Q, Qb
     # complex product = real product on real and imaginary parts
     z = torch.complex(x, y)
     yz = P.matvec(z)
