@@ -8,6 +8,8 @@
 // SelectedCIExpander._find_important_configs (residual_expansion.py:498-522) --
 // there a Python dict keyed by hash(bytes).  fgk_pt2_export is phase 2
 // (:527-548): diagonal of every candidate and coupling^2 / (|E - E_x| + 1e-10).
+#include <stdlib.h>
+
 #include "fgk_internal.cuh"
 
 __device__ __forceinline__ void atomic_max_abs(double* addr, double v)
@@ -89,7 +91,8 @@ __device__ __forceinline__ void warp_enumerate_split(const DetCtx& c, int lane, 
     }
 }
 
-__global__ void __launch_bounds__(FGK_BLOCK)
+template <int BPS>      // resident CTAs per SM the register budget is sized for
+__global__ void __launch_bounds__(FGK_BLOCK, BPS)
 k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_idx,
                  const double* __restrict__ coeff, i64 n_src, int n_split, int mode, unsigned n_pass,
                  unsigned pass_id)
@@ -252,9 +255,24 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
     i64 need = (n_src * n_split + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
     i64 cap = (i64)fgk_sm_count(h->device) * 8;
     int grid = (int)(need < cap ? need : cap);
-    k_pt2_accumulate<<<grid, FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, (unsigned)n_pass,
-        (unsigned)pass_id);
+    // the kernel is bound by random DRAM sectors (hash table): measured identical at 4, 6 and 8
+    // resident CTAs per SM (1.9e9 candidates/s at config-5 shape); FGK_PT2_BPS selects.
+    static int bps = 0;
+    if (!bps) {
+        const char* e = getenv("FGK_PT2_BPS");
+        bps = e ? atoi(e) : 4;
+        if (bps != 4 && bps != 6 && bps != 8) bps = 4;
+    }
+    cap = (i64)fgk_sm_count(h->device) * bps;
+    grid = (int)(need < cap ? need : cap);
+#define FGK_PT2_LAUNCH(B)                                                                          \
+    k_pt2_accumulate<B><<<grid, FGK_BLOCK, 0, (cudaStream_t)stream>>>(                             \
+        h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, (unsigned)n_pass, \
+        (unsigned)pass_id)
+    if (bps == 8) FGK_PT2_LAUNCH(8);
+    else if (bps == 6) FGK_PT2_LAUNCH(6);
+    else FGK_PT2_LAUNCH(4);
+#undef FGK_PT2_LAUNCH
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }
