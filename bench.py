@@ -414,7 +414,7 @@ def run_ours(args):
         coeff[:ns] = torch.exp(-torch.arange(ns, dtype=torch.float64, device=dev) / (0.25 * ns))
         coeff /= torch.linalg.norm(coeff)
         from flow_guided_krylov_b200.expansion import Pt2Workspace, default_pt2_capacity
-        n_local_src = -(-ns // world)
+        n_local_src = -(-ns // world)      # a rank accumulates ~1/world of the candidates
         wsp = Pt2Workspace(default_pt2_capacity(H, n_local_src), dev)   # reused across sweeps, like an expander would
         reps = 3
         sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500, workspace=wsp)   # warm-up sweep
