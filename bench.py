@@ -436,6 +436,24 @@ def run_ours(args):
                        "1 warm-up + 3 timed sweeps, workspace reused"}
         del wsp
 
+    # ---- Stage-1 hook: reference-order connection enumeration (connections/s), rank 0 only ----
+    conn = None
+    if rank == 0 and args.conn_dets > 0:
+        nd = min(args.conn_dets, n)
+        sample = dets[torch.randperm(n, generator=torch.Generator().manual_seed(2))[:nd].to(dev)].contiguous()
+        H.connections_packed(sample[:8])                      # warm-up
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        od, el, srcs, offs = H.connections_packed(sample)
+        c1.record()
+        torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1)
+        conn = {"value": int(od.shape[0]) / (cms * 1e-3), "unit": "connections/s", "dets": nd,
+                "connections": int(od.shape[0]), "ms": cms,
+                "what": "fgk_conn_count + fgk_conn_fill (reference emission order, packed outputs: 28 B/connection)"}
+        del od, el, srcs, offs, sample
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -452,6 +470,19 @@ def run_ours(args):
                          f"{built_nnz / b_s:.3g} H nnz/s = {raw / b_s:.3g} connections/s), tiled with rotated "
                          f"columns to {len(data)} nnz; oracle csr_matvec x{reps} in {el:.1f}s",
                "build_nnz_per_s": built_nnz / b_s, "connections_per_s": raw / b_s}
+        # PT2 phase 1 on the CPU port: 24 sources of the same basis (single thread, like the reference's loop)
+        try:
+            from oracle import oracle as orc
+            O = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), args.n_alpha, args.n_beta)
+            cfg_all = unpack_np(dets_np, args.n_orb)
+            vv = np.zeros(n)
+            vv[:24] = np.linspace(1.0, 0.5, 24)
+            t0 = time.perf_counter()
+            _, _, _, raw_c = O.pt2_candidates(cfg_all, vv)
+            cpu["pt2_candidates_per_s"] = raw_c / (time.perf_counter() - t0)
+            cpu["pt2_sample"] = f"24 sources, {raw_c} candidates, oracle pt2_candidates (1 thread)"
+        except Exception as e:          # the baseline leg must never sink the bench line
+            cpu["pt2_error"] = str(e)[:200]
 
     peak, which = measured_peak()
     bytes_per_launch = 12.0 * nnz_local + 20.0 * P.n_rows
@@ -478,7 +509,7 @@ def run_ours(args):
         "multi_gpu_step": (None if world == 1 else
                            "fused: SELL H.v storing y into every rank's next vector over NVLink peer memory + flag barrier"
                            if fused else "SELL H.v + NCCL all-gather"),
-        "build": build, "pt2": pt2,
+        "build": build, "pt2": pt2, "connections": conn,
     }
     print(json.dumps(line))
     if world > 1:
@@ -506,6 +537,7 @@ def main():
     ap.add_argument("--nccl-allgather", action="store_true",
                     help="N>1: separate NCCL all-gather after the product instead of the fused peer-store kernel")
     ap.add_argument("--pt2-sources", type=int, default=2048)
+    ap.add_argument("--conn-dets", type=int, default=1024, help="determinants of the connection-enumeration leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
