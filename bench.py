@@ -406,6 +406,59 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms, kern_ms, e2e_s = (float(v) for v in tmax)
 
+    # ---- Krylov leg: what Stage 4 does with the operator (Davidson ground state; one Taylor
+    # exp(-i dt H) step on a complex vector), through the same H.v kernels ----------------
+    krylov = None
+    if not args.no_krylov:
+        from flow_guided_krylov_b200.solvers import lowest_eigenpairs, expm_multiply, one_norm
+        calls = [0]
+        if world > 1:
+            kop = fdist.FusedShardedOperator(P) if args.format == "sell" and not args.nccl_allgather \
+                else fdist.ShardedOperator(n, P.matvec, P.diagonal())
+            diag_full = kop.diagonal()
+
+            def kmv(v):
+                calls[0] += 1
+                return kop.matvec(v)
+        else:
+            kop = None
+            diag_full = P.diagonal()
+
+            def kmv(v):
+                calls[0] += 1
+                return P.matvec(v)
+        barrier()
+        t0 = time.perf_counter()
+        w, vec = lowest_eigenpairs(P, k=1, tol=1e-9, matvec=kmv, diagonal=diag_full, dense_max=0)
+        barrier()
+        t_dav = time.perf_counter() - t0
+        res = kmv(vec[:, 0].contiguous()) - w[0] * vec[:, 0]
+        krylov = {"davidson_seconds": t_dav, "davidson_matvecs": calls[0] - 1, "e0": float(w[0]),
+                  "residual_norm": float(torch.linalg.norm(res))}
+        # one SKQD time step (complex vector): N=1 only (the fused operator is real-valued)
+        if world == 1:
+            psi = torch.zeros(n, dtype=torch.complex128, device=dev)
+            psi[0] = 1.0
+            d_ = P.diagonal()
+            mu = float(d_.sum()) / n
+            if P.cols.numel():
+                nrm = float((one_norm(P) - d_.abs() + (d_ - mu).abs()).max())
+            else:
+                nrm = float(d_.abs().max()) * 4
+            zc = [0]
+
+            def zmv(v):
+                zc[0] += 1
+                return P.matvec(v)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            psi1 = expm_multiply(P, psi, -0.1j, matvec=zmv, mu=mu, norm1=nrm)
+            torch.cuda.synchronize()
+            krylov.update(expm_step_seconds=time.perf_counter() - t0, expm_step_matvecs=zc[0],
+                          expm_norm=float(torch.linalg.norm(psi1)))
+        if kop is not None and hasattr(kop, "close"):
+            kop.close()
+
     # ---- PT2 sweep (candidates/s), same Hamiltonian and basis -------------------------
     pt2 = None
     if args.pt2_sources > 0:
@@ -509,7 +562,7 @@ def run_ours(args):
         "multi_gpu_step": (None if world == 1 else
                            "fused: SELL H.v storing y into every rank's next vector over NVLink peer memory + flag barrier"
                            if fused else "SELL H.v + NCCL all-gather"),
-        "build": build, "pt2": pt2, "connections": conn,
+        "build": build, "pt2": pt2, "connections": conn, "krylov": krylov,
     }
     print(json.dumps(line))
     if world > 1:
@@ -536,6 +589,7 @@ def main():
                     help="fill SELL-32 storage directly (half the memory, no CSR copy; the strided fill is ~2.5x slower)")
     ap.add_argument("--nccl-allgather", action="store_true",
                     help="N>1: separate NCCL all-gather after the product instead of the fused peer-store kernel")
+    ap.add_argument("--no-krylov", action="store_true", help="skip the Davidson / expm leg")
     ap.add_argument("--pt2-sources", type=int, default=2048)
     ap.add_argument("--conn-dets", type=int, default=1024, help="determinants of the connection-enumeration leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")

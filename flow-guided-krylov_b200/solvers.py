@@ -24,11 +24,18 @@ def _full_matvec(P, x):
     return P.matvec(x)
 
 
-def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=400, max_space=None, matvec=None,
+def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=None,
                       diagonal=None, dense_max=DENSE_EIG_MAX, v0=None):
     """k lowest eigenpairs of the symmetric operator P (a ProjectedH built with
     H_SYM, or any object with .n plus `matvec`/`diagonal` callables).
-    Returns (w (k,) float64 tensor ascending, V (n,k))."""
+    Returns (w (k,) float64 tensor ascending, V (n,k)).
+
+    Small n: dense eigh on the device.  Otherwise block Davidson with the diagonal
+    preconditioner and THICK restart (the lowest Ritz vectors are kept, H V is rotated
+    along, no extra products); the small projected matrix lives on the host (numpy eigh),
+    so an iteration costs the H.v products plus a handful of n x m device GEMVs and one
+    scalar read-back."""
+    import numpy as np
     n = P.n
     mv = matvec if matvec is not None else (lambda x: _full_matvec(P, x))
     k = min(k, n)
@@ -39,59 +46,68 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=400, max_space=None, matvec=No
     diag = diagonal if diagonal is not None else P.diagonal()
     dev = diag.device
     nb = min(max(2 * k, k + 2), n)                 # initial block: lowest diagonal entries
-    if max_space is None:
-        max_space = max(8 * k, 24)
-    V = torch.zeros(n, nb, dtype=torch.float64, device=dev)
+    m_max = min(n, max_space if max_space is not None else max(12 * k, 36))
+    m_max = max(m_max, nb + k)
+    keep = min(max(2 * k + 2, m_max // 3), m_max - k)
+    V = torch.zeros(n, m_max, dtype=torch.float64, device=dev)
+    W = torch.zeros(n, m_max, dtype=torch.float64, device=dev)
     start = torch.argsort(diag)[:nb]
-    V[start, torch.arange(nb, device=dev)] = 1.0
+    V0 = torch.zeros(n, nb, dtype=torch.float64, device=dev)
+    V0[start, torch.arange(nb, device=dev)] = 1.0
     # A seeded random admixture: unit vectors alone can be orthogonal to a whole
     # symmetry sector (e.g. triplets), which residual norms cannot detect.
     gen = torch.Generator(device="cpu").manual_seed(20240229)
-    V += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen).to(dev)
+    V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen).to(dev)
     if v0 is not None:
-        V[:, 0] = v0.to(dev, torch.float64)
-    V, _ = torch.linalg.qr(V)
-    W = torch.stack([mv(V[:, i].contiguous()) for i in range(V.shape[1])], dim=1)
-    w = X = None
+        V0[:, 0] = v0.to(dev, torch.float64)
+    V0, _ = torch.linalg.qr(V0)
+    m = nb
+    V[:, :m] = V0
+    for i in range(m):
+        W[:, i] = mv(V[:, i].contiguous())
+    T = np.zeros((m_max, m_max))
+    T[:m, :m] = (V[:, :m].T @ W[:, :m]).cpu().numpy()
+    w_out = X = None
     for _ in range(max_iter):
-        T = V.T @ W
-        T = 0.5 * (T + T.T)
-        th, s = torch.linalg.eigh(T)
-        th, s = th[:k], s[:, :k]
-        X = V @ s
-        R = W @ s - X * th
-        rn = torch.linalg.norm(R, dim=0)
-        w = th
-        scale = max(1.0, float(th.abs().max()))
-        if float(rn.max()) < tol * scale:
+        Tm = 0.5 * (T[:m, :m] + T[:m, :m].T)
+        th, s = np.linalg.eigh(Tm)
+        s_dev = torch.from_numpy(np.ascontiguousarray(s)).to(dev)
+        thk = torch.from_numpy(th[:k].copy()).to(dev)
+        X = V[:, :m] @ s_dev[:, :k]
+        R = W[:, :m] @ s_dev[:, :k] - X * thk
+        rn = torch.linalg.norm(R, dim=0).cpu().numpy()
+        w_out = thk
+        scale = max(1.0, float(np.abs(th[:k]).max()))
+        if rn.max() < tol * scale:
             break
-        # Davidson correction with the diagonal preconditioner
-        new = []
-        for i in range(k):
-            if float(rn[i]) < tol * scale:
-                continue
-            den = th[i] - diag
+        todo = [i for i in range(k) if rn[i] >= tol * scale]
+        if m + len(todo) > m_max:                   # thick restart: rotate V and H V together
+            q = keep
+            V[:, :q] = V[:, :m] @ s_dev[:, :q]
+            W[:, :q] = W[:, :m] @ s_dev[:, :q]
+            T[:] = 0.0
+            T[np.arange(q), np.arange(q)] = th[:q]
+            m = q
+        added = 0
+        for i in todo:
+            den = thk[i] - diag
             den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
-            new.append(R[:, i] / den)
-        if V.shape[1] + len(new) > max_space:       # thick restart on the Ritz vectors
-            V = X.clone()
-            V, _ = torch.linalg.qr(V)
-            W = torch.stack([mv(V[:, i].contiguous()) for i in range(V.shape[1])], dim=1)
-        added = []
-        for t in new:
-            for _ in range(2):                       # CGS2
-                t = t - V @ (V.T @ t)
-                for a in added:
-                    t = t - a * torch.dot(a, t)
+            t = R[:, i] / den
+            for _ in range(2):                      # CGS2 against everything kept so far
+                t = t - V[:, :m + added] @ (V[:, :m + added].T @ t)
             nt = float(torch.linalg.norm(t))
             if nt > 1e-10:
-                added.append(t / nt)
-        if not added:
+                V[:, m + added] = t / nt
+                added += 1
+        if added == 0:
             break
-        A = torch.stack(added, dim=1)
-        V = torch.cat([V, A], dim=1)
-        W = torch.cat([W, torch.stack([mv(A[:, i].contiguous()) for i in range(A.shape[1])], dim=1)], dim=1)
-    return w.clone(), X.clone()
+        for j in range(m, m + added):
+            W[:, j] = mv(V[:, j].contiguous())
+        blk = (V[:, :m + added].T @ W[:, m:m + added]).cpu().numpy()     # new columns of T
+        T[:m + added, m:m + added] = blk
+        T[m:m + added, :m + added] = blk.T
+        m += added
+    return w_out.clone(), X.clone()
 
 
 # Al-Mohy & Higham 2011, table 3.1 (tol = 2^-53): theta_m for selected m
