@@ -1,0 +1,74 @@
+"""Drop-in check against the reference's own classes (runs only where /root/reference
+exists, i.e. the build container): every mirrored method keeps the reference's parameter
+names, order and defaults; config dataclasses keep the reference's fields and defaults."""
+import dataclasses
+import inspect
+import os
+import sys
+
+import pytest
+
+REF = os.environ.get("FGK_REFERENCE_SRC", "/root/reference/src")
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present")
+
+
+@pytest.fixture(scope="module")
+def mods():
+    sys.path.insert(0, REF)
+    import hamiltonians.molecular as rm
+    import krylov.residual_expansion as rx
+    import krylov.skqd as rs
+    import flow_guided_krylov_b200 as f
+    return rm, rx, rs, f
+
+
+def _params(fn):
+    # the reference's `device` default is "cuda" if torch.cuda.is_available() else "cpu": machine dependent
+    return [(p.name, "<device>" if p.name == "device" else p.default)
+            for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+
+
+def _assert_superset(ref_fn, my_fn, what):
+    rp, mp = _params(ref_fn), _params(my_fn)
+    assert mp[:len(rp)] == rp, f"{what}: reference {rp} vs ours {mp}"
+    for name, default in mp[len(rp):]:
+        assert default is not inspect.Parameter.empty, f"{what}: extra parameter {name} needs a default"
+
+
+def test_hamiltonian_interface(mods):
+    rm, _, _, f = mods
+    for m in ["__init__", "diagonal_elements_batch", "diagonal_element", "get_connections",
+              "get_all_connections_with_indices", "get_connections_parallel", "matrix_elements_fast",
+              "matrix_elements", "get_sparse_matrix_elements", "get_hf_state", "fci_energy", "_config_to_index"]:
+        _assert_superset(getattr(rm.MolecularHamiltonian, m), getattr(f.MolecularHamiltonian, m),
+                         f"MolecularHamiltonian.{m}")
+    # the hook utils/connection_cache.py:250 looks for (the reference itself does not define it)
+    assert hasattr(f.MolecularHamiltonian, "get_connections_batch")
+    assert [x.name for x in dataclasses.fields(rm.MolecularIntegrals)] == \
+           [x.name for x in dataclasses.fields(f.MolecularIntegrals)]
+
+
+def test_expander_interface(mods):
+    _, rx, _, f = mods
+    for cls in ("SelectedCIExpander", "ResidualBasedExpander"):
+        for m in ["__init__", "expand_basis", "_diagonalize"]:
+            _assert_superset(getattr(getattr(rx, cls), m), getattr(getattr(f, cls), m), f"{cls}.{m}")
+    _assert_superset(rx.SelectedCIExpander._find_important_configs,
+                     f.SelectedCIExpander._find_important_configs, "_find_important_configs")
+    ref = {x.name: x.default for x in dataclasses.fields(rx.ResidualExpansionConfig)}
+    mine = {x.name: x.default for x in dataclasses.fields(f.ResidualExpansionConfig)}
+    assert ref == mine
+
+
+def test_skqd_interface(mods):
+    _, _, rs, f = mods
+    for m in ["__init__", "generate_krylov_samples", "build_cumulative_basis", "get_basis_states",
+              "compute_ground_state_energy", "run"]:
+        _assert_superset(getattr(rs.SampleBasedKrylovDiagonalization, m),
+                         getattr(f.SampleBasedKrylovDiagonalization, m), f"SKQD.{m}")
+    for m in ["__init__", "get_combined_basis", "run_with_nf"]:
+        _assert_superset(getattr(rs.FlowGuidedSKQD, m), getattr(f.FlowGuidedSKQD, m), f"FlowGuidedSKQD.{m}")
+    ref = {x.name: x.default for x in dataclasses.fields(rs.SKQDConfig)}
+    mine = {x.name: x.default for x in dataclasses.fields(f.SKQDConfig)}
+    for k, v in ref.items():
+        assert k in mine and mine[k] == v, f"SKQDConfig.{k}"

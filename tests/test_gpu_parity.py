@@ -683,3 +683,40 @@ def test_error_conventions(fgk):
     z = x + 1j * x[::-1]
     yz = P.matvec(torch.from_numpy(z).cuda()).cpu().numpy()
     assert np.array_equal(P.matvec_host(torch.from_numpy(z)).numpy(), yz)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_on_device(fgk, seed):
+    """random orbital counts / fillings (incl. empty and full spin blocks), non-symmetric and
+    sparsified integrals: connections, diagonal, projected H (both builders) and PT2 vs the oracle"""
+    from oracle import oracle as orc
+    from test_hostcheck import _random_case
+    n_orb, na, nb, h1, g, rng = _random_case(seed)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, g, 0.3, na + nb, n_orb, na, nb), "cuda:0")
+    O = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), na, nb, 0.3)
+    dets = np.unique(random_dets(n_orb, na, nb, 14, rng), axis=0)
+    c, e, src = H.get_connections_batch(t64(dets))
+    oc, oe, osrc, _ = O.connections_batch(dets)
+    assert c.shape[0] == len(oc)
+    if len(oc):
+        assert np.array_equal(c.cpu().numpy().astype(np.uint8), oc)
+        assert np.array_equal(e.cpu().numpy().view(np.uint32), oe.view(np.uint32))
+        assert np.array_equal(src.cpu().numpy(), osrc)
+    assert np.abs(H.diagonal_elements_batch(t64(dets)).cpu().numpy() - O.diag(dets)).max() < TOL
+    n = len(dets)
+    D = O.dense_H(dets)
+    off = ~np.eye(n, dtype=bool)
+    for mode, ref in ((fgk.H_RAW, D), (fgk.H_SYM, 0.5 * (D + D.T))):
+        for flag in (0, fgk.H_FLAT_WALK):
+            A = H.projected_csr(t64(dets), mode | flag).to_scipy().toarray()
+            assert np.array_equal(A[off], ref[off])
+            assert np.abs(np.diag(A) - np.diag(ref)).max() < TOL
+    v = rng.standard_normal(n)
+    cand_o, _, c64, raw = O.pt2_candidates(dets, v)
+    cand, cpl, dg, imp, st = fgk.pt2_candidates(H, fgk.BasisIndex(H.pack(t64(dets))),
+                                                torch.from_numpy(v).cuda(), -1.0)
+    assert st["raw_candidates"] == raw and cand.shape[0] == len(cand_o)
+    if len(cand_o):
+        got = {bytes(r): i for i, r in enumerate(unpack_np(dets_np(cand), n_orb))}
+        perm = np.array([got[bytes(r)] for r in cand_o])
+        assert np.abs(cpl.cpu().numpy()[perm] - c64).max() < 1e-12

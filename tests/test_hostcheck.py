@@ -167,3 +167,58 @@ def test_split_value_and_fast_parity_equal_generic_elements(name):
     pk = pack_np(dets, n_orb)
     assert hostcheck().hc_check_split(hc, _p(pk), len(pk)) == 0
     hostcheck().hc_ham_destroy(hc)
+
+
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    n_orb = int(rng.integers(2, 10))
+    na = int(rng.integers(0, n_orb + 1))
+    nb = int(rng.integers(0, n_orb + 1))
+    h1 = rng.standard_normal((n_orb, n_orb)); h1 = 0.5 * (h1 + h1.T)
+    g = rng.standard_normal((n_orb,) * 4) * 0.2
+    if seed % 2:                                   # 8-fold symmetric half of the time
+        g = g + g.transpose(1, 0, 2, 3); g = g + g.transpose(0, 1, 3, 2); g = g + g.transpose(2, 3, 0, 1)
+    if seed % 3 == 0:                              # zeros so that the 1e-12 filters act
+        h1[rng.random(h1.shape) < 0.4] = 0.0
+        g[rng.random(g.shape) < 0.5] = 0.0
+    return n_orb, na, nb, h1, g, rng
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_against_oracle(seed):
+    """random orbital counts / fillings (incl. empty and full spin blocks), NON-symmetric
+    integrals and sparsified tables: enumeration, diagonal and both row builders vs the oracle"""
+    from helpers import random_dets
+    n_orb, na, nb, h1, g, rng = _random_case(seed)
+    hc = hostcheck().hc_ham_create(_p(np.ascontiguousarray(h1)), _p(np.ascontiguousarray(g)), n_orb, na, nb, 0.3)
+    H = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), na, nb, 0.3)
+    dets = np.unique(random_dets(n_orb, na, nb, 12, rng), axis=0)
+    pk = pack_np(dets, n_orb)
+    out = np.zeros(len(pk))
+    hostcheck().hc_diag(hc, _p(pk), len(pk), _p(out))
+    assert np.abs(out - H.diag(dets)).max() < 1e-9
+    for j in range(len(pk)):
+        oc, oe = H.connections(dets[j])
+        cap = len(oc) + 4
+        od, el = np.zeros((cap, 2), np.uint64), np.zeros(cap, np.float32)
+        m = hostcheck().hc_connections(hc, int(pk[j, 0]), int(pk[j, 1]), _p(od), _p(el), cap)
+        assert m == len(oc)
+        assert np.array_equal(unpack_np(od[:m], n_orb), oc)
+        assert np.array_equal(el[:m].view(np.uint32), oe.view(np.uint32))
+    assert hostcheck().hc_check_split(hc, _p(pk), len(pk)) == 0
+    n = len(dets)
+    D = H.dense_H(dets)
+    for mode, ref in ((0, D), (1, 0.5 * (D + D.T))):
+        for builder in (0, 1, 2):
+            got = np.zeros_like(D)
+            for i in range(n):
+                cap = n + 4
+                c, v = np.zeros(cap, np.int32), np.zeros(cap)
+                if builder == 0:
+                    m = hostcheck().hc_bra_row(hc, _p(pk), n, i, mode, _p(c), _p(v), cap)
+                else:
+                    m = hostcheck().hc_bra_row2(hc, _p(pk), n, i, mode, builder - 1, _p(c), _p(v), cap)
+                got[i, c[:m]] = v[:m]
+            off = ~np.eye(n, dtype=bool)
+            assert np.array_equal(got[off], ref[off])
+    hostcheck().hc_ham_destroy(hc)
