@@ -466,9 +466,9 @@ def run_ours(args):
         coeff = torch.zeros(n, dtype=torch.float64, device=dev)
         coeff[:ns] = torch.exp(-torch.arange(ns, dtype=torch.float64, device=dev) / (0.25 * ns))
         coeff /= torch.linalg.norm(coeff)
-        from flow_guided_krylov_b200.expansion import Pt2Workspace, default_pt2_capacity
+        from flow_guided_krylov_b200.expansion import default_pt2_workspace
         n_local_src = -(-ns // world)      # a rank accumulates ~1/world of the candidates
-        wsp = Pt2Workspace(default_pt2_capacity(H, n_local_src), dev)   # reused across sweeps, like an expander would
+        wsp = default_pt2_workspace(H, n_local_src, partition=not args.pt2_direct)   # reused across sweeps
         reps = 3
         sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500, workspace=wsp)   # warm-up sweep
         barrier()
@@ -484,7 +484,7 @@ def run_ours(args):
         pt2 = {"value": st["raw_candidates_total"] / (float(pms[0]) * 1e-3), "unit": "PT2 candidates/s",
                "raw_candidates": st["raw_candidates_total"], "sources": ns, "ms": float(pms[0]),
                "passes": st["passes"], "selected": int(sel.shape[0]),
-               "unique_candidates": st["unique_total"],
+               "unique_candidates": st["unique_total"], "partition": getattr(wsp, "partition", None),
                "what": "enumerate -> filter -> hash-accumulate -> diagonal -> importance -> top-500, "
                        "1 warm-up + 3 timed sweeps, workspace reused"}
         del wsp
@@ -591,6 +591,8 @@ def main():
                     help="N>1: separate NCCL all-gather after the product instead of the fused peer-store kernel")
     ap.add_argument("--no-krylov", action="store_true", help="skip the Davidson / expm leg")
     ap.add_argument("--pt2-sources", type=int, default=2048)
+    ap.add_argument("--pt2-direct", action="store_true",
+                    help="PT2: upsert straight into the hash map (no radix partition in front)")
     ap.add_argument("--conn-dets", type=int, default=1024, help="determinants of the connection-enumeration leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=256)

@@ -13,7 +13,7 @@ from ._native import H_DROP_ZEROS, H_FLAT_WALK, H_RAW, H_SYM, PT2_MAXABS, PT2_SU
 from .hamiltonian import (BasisIndex, MolecularHamiltonian, MolecularIntegrals,  # noqa: F401
                           ProjectedH, sort_unique_dets)
 from .expansion import (Pt2Workspace, ResidualBasedExpander, ResidualExpansionConfig,  # noqa: F401
-                        SelectedCIExpander, pt2_candidates, pt2_select, select_top_k)
+                        SelectedCIExpander, default_pt2_workspace, pt2_candidates, pt2_select, select_top_k)
 from .skqd import FlowGuidedSKQD, SampleBasedKrylovDiagonalization, SKQDConfig  # noqa: F401
 from .solvers import expm_multiply, lowest_eigenpairs  # noqa: F401
 

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "fgk_peer_barrier": (ci, [C.POINTER(vp), ci, ci, C.c_uint64, vp, ci, vp]),
     "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, vp, ci, C.POINTER(vp)]),
     "fgk_pt2_destroy": (ci, [vp]),
+    "fgk_pt2_set_partition": (ci, [vp, ci, ci, i64, vp, vp, vp]),
     "fgk_pt2_reset": (ci, [vp, vp]),
     "fgk_pt2_accumulate": (ci, [vp, vp, vp, vp, vp, i64, ci, ci, ci, vp]),
     "fgk_pt2_merge": (ci, [vp, vp, vp, i64, ci, vp]),

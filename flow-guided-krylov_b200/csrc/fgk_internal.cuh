@@ -61,11 +61,23 @@ struct fgk_index {
 
 struct Pt2View {
     u64* table;         // (tag << 32 | slot), empty = ~0
-    u64 mask;
+    u64 mask;           // table_slots - 1
     fgk_det* keys;      // pool
     double* sums;
     i64 capacity;
     unsigned long long* counters;   // [0] slots used, [1] raw candidates tested, [2] overflow
+    // The table is split into 2^region_bits regions selected by the TOP hash bits; linear
+    // probing stays inside a region.  With region_bits = 0 it is one flat table.
+    int region_bits;
+    u64 region_mask;    // (table_slots >> region_bits) - 1
+    // Optional partition queues (radix partition before the hash): 2^queue_bits queues selected
+    // by the top hash bits (queue_bits >= region_bits, so queue order is region order), each
+    // `qstride` (determinant, value) pairs long; qcursors[q] = pairs appended to queue q.
+    int queue_bits;
+    i64 qstride;
+    fgk_det* qdets;
+    double* qvals;
+    unsigned long long* qcursors;
 };
 
 struct fgk_pt2 {

@@ -22,10 +22,15 @@ __device__ __forceinline__ void atomic_max_abs(double* addr, double v)
 // insert-or-accumulate; returns false on pool overflow
 __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, double val, int mode)
 {
-    u64 tag = h >> 32, slot = h & W.mask;
+    const u64 tag = h >> 32;
+    const u64 base = W.region_bits ? (h >> (64 - W.region_bits)) * (W.region_mask + 1) : 0;
+    u64 local = (h >> 7) & W.region_mask;
+    u64 slot = base + local;
+    u64 probes = 0;
     long long mine = -1;        // pool slot this thread allocated (at most one)
     bool ok = true;
     while (true) {
+        if (++probes > W.region_mask + 1) { atomicExch(W.counters + 2, 1ull); ok = false; break; }   // region full
         u64 e = *reinterpret_cast<volatile u64*>(W.table + slot);
         if (e == FGK_EMPTY) {
             if (mine < 0) {
@@ -54,7 +59,8 @@ __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, d
                 break;
             }
         }
-        slot = (slot + 1) & W.mask;
+        local = (local + 1) & W.region_mask;
+        slot = base + local;
     }
     if (mine >= 0 && mine < W.capacity)   // allocated but lost the race: mark the slot dead
         reinterpret_cast<ulonglong2*>(W.keys)[mine] = make_ulonglong2(FGK_EMPTY, FGK_EMPTY);
@@ -91,7 +97,26 @@ __device__ __forceinline__ void warp_enumerate_split(const DetCtx& c, int lane, 
     }
 }
 
-template <int BPS>      // resident CTAs per SM the register budget is sized for
+// append (determinant, value) to the partition queue chosen by the top hash bits; called by
+// all 32 lanes (push = false for idle lanes); one cursor atomic per distinct queue per warp
+__device__ __forceinline__ void pt2_queue_push(const Pt2View& W, bool push, fgk_det o, u64 h, double val,
+                                               int lane)
+{
+    const unsigned q = push ? (unsigned)(h >> (64 - W.queue_bits)) : (0x80000000u | (unsigned)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, q);
+    if (!push) return;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(W.qcursors + q, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const i64 pos = (i64)base + __popc(peers & ((1u << lane) - 1u));
+    if (pos >= W.qstride) { atomicExch(W.counters + 2, 1ull); return; }
+    const i64 at = (i64)q * W.qstride + pos;
+    reinterpret_cast<ulonglong2*>(W.qdets)[at] = make_ulonglong2(o.a, o.b);
+    W.qvals[at] = val;
+}
+
+template <int BPS, bool QUEUE>      // BPS: resident CTAs per SM the register budget is sized for
 __global__ void __launch_bounds__(FGK_BLOCK, BPS)
 k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_idx,
                  const double* __restrict__ coeff, i64 n_src, int n_split, int mode, unsigned n_pass,
@@ -114,15 +139,21 @@ k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_
         DetCtx c;
         warp_build_ctx(c, H.n_orb, d, s_lists[wib], lane);
         auto visit = [&](bool valid, const Excitation& x) {
-            if (!valid) return;
-            float el;
-            if (!ket_element_fast(H, d, x, ldf, el)) return;          // reference filter
-            fgk_det o = apply_excitation(d, c.n, x);
-            const u64 h = det_hash(o.a, o.b);
-            if (n_pass > 1 && (unsigned)((h >> 40) % n_pass) != pass_id) return;
-            tested++;
-            if (index_find_filtered_h(I, o, h, x.cls) >= 0) return;   // in the basis (:513)
-            pt2_upsert(W, o, h, cj * (double)el, mode);
+            float el = 0.f;
+            fgk_det o = d;
+            u64 h = 0;
+            bool push = valid && ket_element_fast(H, d, x, ldf, el);  // reference filter
+            if (push) {
+                o = apply_excitation(d, c.n, x);
+                h = det_hash(o.a, o.b);
+                if (n_pass > 1 && (unsigned)((h >> 40) % n_pass) != pass_id) push = false;
+            }
+            if (push) {
+                tested++;
+                if (index_find_filtered_h(I, o, h, x.cls) >= 0) push = false;   // in the basis (:513)
+            }
+            if (QUEUE) pt2_queue_push(W, push, o, h, cj * (double)el, lane);
+            else if (push) pt2_upsert(W, o, h, cj * (double)el, mode);
         };
         warp_enumerate_split(
             c, lane, split, n_split,
@@ -147,6 +178,28 @@ k_pt2_merge(Pt2View W, const fgk_det* __restrict__ dets, const double* __restric
         ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + i);
         fgk_det o = {d.x, d.y};
         pt2_upsert(W, o, det_hash(o.a, o.b), __ldg(vals + i), mode);
+    }
+}
+
+// second half of the partitioned sweep: walk the queues in queue (= table region) order and
+// upsert; the CTAs that run together work on neighbouring queues, whose table region and
+// freshly allocated pool slots stay L2-resident instead of being random DRAM sectors.
+__global__ void __launch_bounds__(256)
+k_pt2_aggregate(Pt2View W, int mode, i64 per_block)
+{
+    const i64 total = ((i64)1 << W.queue_bits) * W.qstride;
+    const i64 lo = (i64)blockIdx.x * per_block;
+    const i64 hi = lo + per_block < total ? lo + per_block : total;
+    for (i64 s0 = lo; s0 < hi; s0 += blockDim.x) {
+        const i64 s = s0 + threadIdx.x;
+        if (s >= hi) continue;
+        const i64 q = s / W.qstride, idx = s - q * W.qstride;
+        unsigned long long cnt = W.qcursors[q];
+        if (cnt > (unsigned long long)W.qstride) cnt = (unsigned long long)W.qstride;
+        if ((unsigned long long)idx >= cnt) continue;
+        ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(W.qdets) + s);
+        fgk_det o = {d.x, d.y};
+        pt2_upsert(W, o, det_hash(o.a, o.b), __ldg(W.qvals + s), mode);
     }
 }
 
@@ -216,7 +269,37 @@ extern "C" int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* t
     P->v.keys = (fgk_det*)keys;
     P->v.sums = sums;
     P->v.counters = (unsigned long long*)counters;
+    P->v.region_bits = 0;
+    P->v.region_mask = P->v.mask;
+    P->v.queue_bits = 0;
+    P->v.qstride = 0;
+    P->v.qdets = nullptr; P->v.qvals = nullptr; P->v.qcursors = nullptr;
     *out = P;
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_set_partition(fgk_pt2_t ws, int region_bits, int queue_bits, int64_t queue_stride,
+                                     uint64_t* queue_dets, double* queue_vals, uint64_t* queue_cursors)
+{
+    if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_set_partition: null handle");
+    if (queue_bits == 0) {          // back to the direct (unpartitioned) sweep
+        ws->v.region_bits = 0; ws->v.region_mask = ws->v.mask;
+        ws->v.queue_bits = 0; ws->v.qstride = 0;
+        ws->v.qdets = nullptr; ws->v.qvals = nullptr; ws->v.qcursors = nullptr;
+        return FGK_OK;
+    }
+    if (region_bits < 0 || queue_bits < region_bits || queue_bits > 20 || queue_stride < 1 ||
+        !queue_dets || !queue_vals || !queue_cursors || ((uintptr_t)queue_dets & 15))
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_set_partition: bad argument");
+    if (((ws->v.mask + 1) >> region_bits) < 64)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_set_partition: table regions would be smaller than 64 slots");
+    ws->v.region_bits = region_bits;
+    ws->v.region_mask = ((ws->v.mask + 1) >> region_bits) - 1;
+    ws->v.queue_bits = queue_bits;
+    ws->v.qstride = queue_stride;
+    ws->v.qdets = (fgk_det*)queue_dets;
+    ws->v.qvals = queue_vals;
+    ws->v.qcursors = (unsigned long long*)queue_cursors;
     return FGK_OK;
 }
 
@@ -234,6 +317,8 @@ extern "C" int fgk_pt2_reset(fgk_pt2_t ws, void* stream)
     FGK_CUDA(cudaMemsetAsync(ws->v.table, 0xFF, (ws->v.mask + 1) * sizeof(u64), st));
     FGK_CUDA(cudaMemsetAsync(ws->v.sums, 0, (size_t)ws->v.capacity * sizeof(double), st));
     FGK_CUDA(cudaMemsetAsync(ws->v.counters, 0, 4 * sizeof(unsigned long long), st));
+    if (ws->v.queue_bits)
+        FGK_CUDA(cudaMemsetAsync(ws->v.qcursors, 0, sizeof(unsigned long long) << ws->v.queue_bits, st));
     return FGK_OK;
 }
 
@@ -265,13 +350,28 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
     }
     cap = (i64)fgk_sm_count(h->device) * bps;
     grid = (int)(need < cap ? need : cap);
-#define FGK_PT2_LAUNCH(B)                                                                          \
-    k_pt2_accumulate<B><<<grid, FGK_BLOCK, 0, (cudaStream_t)stream>>>(                             \
+#define FGK_PT2_LAUNCH(B, Q)                                                                       \
+    k_pt2_accumulate<B, Q><<<grid, FGK_BLOCK, 0, (cudaStream_t)stream>>>(                          \
         h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, (unsigned)n_pass, \
         (unsigned)pass_id)
-    if (bps == 8) FGK_PT2_LAUNCH(8);
-    else if (bps == 6) FGK_PT2_LAUNCH(6);
-    else FGK_PT2_LAUNCH(4);
+    if (ws->v.queue_bits) {
+        // partitioned sweep: enumerate -> append to the queue of the candidate's top hash bits,
+        // then aggregate queue by queue (L2-resident table regions)
+        FGK_PT2_LAUNCH(4, true);
+        FGK_LAUNCH_CHECK();
+        const i64 total = ((i64)1 << ws->v.queue_bits) * ws->v.qstride;
+        const i64 per_block = 256 * 16;
+        const i64 blocks = (total + per_block - 1) / per_block;
+        if (blocks > 0x7fffffffll) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_pt2_accumulate: queue too large");
+        k_pt2_aggregate<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ws->v, mode, per_block);
+        FGK_LAUNCH_CHECK();
+        // the queues are transient: empty them so that a second accumulate call starts clean
+        FGK_CUDA(cudaMemsetAsync(ws->v.qcursors, 0, sizeof(unsigned long long) << ws->v.queue_bits,
+                                 (cudaStream_t)stream));
+    }
+    else if (bps == 8) FGK_PT2_LAUNCH(8, false);
+    else if (bps == 6) FGK_PT2_LAUNCH(6, false);
+    else FGK_PT2_LAUNCH(4, false);
 #undef FGK_PT2_LAUNCH
     FGK_LAUNCH_CHECK();
     return FGK_OK;

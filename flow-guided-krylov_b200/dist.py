@@ -180,7 +180,7 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
     Returns (selected dets, scores, stats); identical on all ranks.  With one rank this is
     expansion.pt2_select."""
     from . import _native as nat
-    from .expansion import (Pt2Workspace, _raw_connections_per_det, default_pt2_capacity,
+    from .expansion import (Pt2Workspace, _raw_connections_per_det, default_pt2_workspace,
                             pt2_select, select_top_k)
     mode = nat.PT2_SUM if mode is None else mode
     rank, ws = world()
@@ -199,12 +199,14 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
     empty = (torch.empty(0, 2, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.float64, device=dev))
     if n_src == 0:
         return empty + (dict(n_sources=0, raw_candidates=0, passes=1, raw_candidates_total=0, unique_total=0),)
-    wa = workspace if workspace is not None else Pt2Workspace(
-        default_pt2_capacity(ham, -(-n_src // ws)), dev)
+    wa = workspace if workspace is not None else default_pt2_workspace(ham, -(-n_src // ws))
     # every rank must run the same number of bucket passes: size them for the smallest workspace
     cap = int(-allreduce_scalar(-float(wa.capacity), "max", dev))
     raw_ub = n_src * _raw_connections_per_det(ham)
     local_passes = max(1, -(-raw_ub // (2 * cap * ws)))
+    qp = int(-allreduce_scalar(-float(wa.queue_pairs), "max", dev))
+    if qp:
+        local_passes = max(local_passes, -(-raw_ub // (qp * ws)))
     while True:
         keep_d, keep_s, raw, uniq, ok = [], [], 0, 0, True
         n_pass = ws * local_passes

@@ -36,7 +36,12 @@ class ResidualExpansionConfig:
 class Pt2Workspace:
     """Device hash map candidate -> FP64 accumulator (fgk_pt2_*)."""
 
-    def __init__(self, capacity, device):
+    L2_REGION_BYTES = 24 << 20      # table region + its pool share that should stay L2-resident
+
+    def __init__(self, capacity, device, queue_pairs=None):
+        """capacity: distinct candidates the map can hold.  queue_pairs: size of the radix
+        partition in front of the hash (pairs per accumulate call); None = no partition,
+        'auto' = 2 x capacity when the accumulator is much larger than L2."""
         self.capacity = int(capacity)
         self.device = device
         slots = 1
@@ -53,6 +58,25 @@ class Pt2Workspace:
             self.capacity, slots, nat.ptr(self._table), nat.ptr(self._keys), nat.ptr(self._sums),
             nat.ptr(self._counters), nat.device_index(device), C.byref(h)))
         self._h = h
+        self.queue_pairs = 0
+        foot = 8 * slots + 24 * self.capacity
+        if queue_pairs == "auto":
+            queue_pairs = 2 * self.capacity if foot > 4 * self.L2_REGION_BYTES else None
+        if queue_pairs:
+            region_bits = 0
+            while (foot >> region_bits) > self.L2_REGION_BYTES and (slots >> (region_bits + 1)) >= 4096:
+                region_bits += 1
+            queue_bits = max(region_bits, 10)
+            nq = 1 << queue_bits
+            stride = int(1.25 * int(queue_pairs) / nq) + 256
+            self._qdets = torch.empty(nq * stride, 2, dtype=torch.int64, device=device)
+            self._qvals = torch.empty(nq * stride, dtype=torch.float64, device=device)
+            self._qcur = torch.zeros(nq, dtype=torch.int64, device=device)
+            nat.check(nat.lib().fgk_pt2_set_partition(
+                self._h, region_bits, queue_bits, stride, nat.ptr(self._qdets), nat.ptr(self._qvals),
+                nat.ptr(self._qcur)))
+            self.queue_pairs = int(queue_pairs)
+            self.partition = dict(region_bits=region_bits, queue_bits=queue_bits, stride=stride)
         self.reset()
 
     def __del__(self):
@@ -158,8 +182,10 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
         return empty + (stats,)
     ws = workspace
     if ws is None:
-        ws = Pt2Workspace(default_pt2_capacity(ham, int(src.numel())), dev)
+        ws = default_pt2_workspace(ham, int(src.numel()))
     n_pass = 1
+    if ws.queue_pairs:
+        n_pass = max(1, -(-int(src.numel()) * _raw_connections_per_det(ham) // ws.queue_pairs))
     while True:
         outs, raw, ok = [], 0, True
         for p in range(n_pass):
@@ -183,13 +209,19 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
     return tuple(torch.cat([o[i] for o in outs]) for i in range(4)) + (stats,)
 
 
-def default_pt2_capacity(ham, n_sources):
-    """pool slots for a sweep over n_sources determinants: every raw connection could be a
-    distinct candidate; bounded by the free HBM (56 B per slot for table + pool, 24-40 B per
-    slot for the export buffers)."""
+def default_pt2_capacity(ham, n_sources, partition=True):
+    """distinct-candidate capacity for a sweep over n_sources determinants: every raw
+    connection could be a distinct candidate; bounded by the free HBM.  Per unit of capacity:
+    16 B table + 24 B pool + 24 B export buffers, plus 2 x 30 B of partition queue."""
     n_conn = _raw_connections_per_det(ham)
     free = nat.device_info(ham.device)["free_bytes"]
-    return int(min(max(4096, 1.05 * n_sources * n_conn), 0.8 * free / 96, 2 ** 31))
+    per = 64 + (60 if partition else 0) + 8
+    return int(min(max(4096, 1.05 * n_sources * n_conn), 0.8 * free / per, 2 ** 31))
+
+
+def default_pt2_workspace(ham, n_sources, partition=True):
+    cap = default_pt2_capacity(ham, n_sources, partition)
+    return Pt2Workspace(cap, ham.device, queue_pairs="auto" if partition else None)
 
 
 def pt2_select(ham, index, coeffs, energy, k, workspace=None, mode=nat.PT2_SUM, coeff_cut=1e-8,
@@ -208,11 +240,13 @@ def pt2_select(ham, index, coeffs, energy, k, workspace=None, mode=nat.PT2_SUM, 
     if src.numel() == 0:
         return (torch.empty(0, 2, dtype=torch.int64, device=dev),
                 torch.empty(0, dtype=torch.float64, device=dev), stats)
-    ws = workspace if workspace is not None else Pt2Workspace(
-        default_pt2_capacity(ham, int(src.numel())), dev)
-    # first guess: half of the raw connections are distinct candidates
+    ws = workspace if workspace is not None else default_pt2_workspace(ham, int(src.numel()))
+    # first guess: half of the raw connections are distinct candidates; with a partition queue
+    # every raw candidate of a pass must also fit the queue
     raw_ub = int(src.numel()) * _raw_connections_per_det(ham)
     n_pass = max(1, -(-raw_ub // (2 * ws.capacity)))
+    if ws.queue_pairs:
+        n_pass = max(n_pass, -(-raw_ub // ws.queue_pairs))
     while True:
         keep_d, keep_s, raw, uniq, ok = [], [], 0, 0, True
         for p in range(n_pass):

@@ -188,6 +188,16 @@ int fgk_peer_barrier(uint64_t* const* peer_flags, int rank, int world, uint64_t 
 int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* keys,
                    double* sums, uint64_t* counters, int device, fgk_pt2_t* out);
 int fgk_pt2_destroy(fgk_pt2_t ws);
+/* Optional radix partition in front of the hash (large sweeps, whose accumulator is far
+ * bigger than L2): the table is split into 2^region_bits regions chosen by the top hash bits
+ * and fgk_pt2_accumulate first appends every candidate to one of 2^queue_bits queues
+ * (queue_bits >= region_bits; queue_stride pairs each: queue_dets uint64[2^queue_bits *
+ * stride][2], queue_vals double[...], queue_cursors uint64[2^queue_bits], all caller memory),
+ * then folds the queues into the table in queue order, so that the table region and pool
+ * slots being written are L2-resident.  Call with queue_bits = 0 to go back to the direct sweep.
+ * Must be followed by fgk_pt2_reset. */
+int fgk_pt2_set_partition(fgk_pt2_t ws, int region_bits, int queue_bits, int64_t queue_stride,
+                          uint64_t* queue_dets, double* queue_vals, uint64_t* queue_cursors);
 int fgk_pt2_reset(fgk_pt2_t ws, void* stream);
 /* For every source s in [0,n_src): j = src_idx[s] (basis position), coefficient
  * coeff[s]; every connection x of basis[j] with x not in the basis adds

@@ -250,8 +250,14 @@ def test_pt2_candidates_and_selection(fgk, name):
         imp_o = c64 ** 2 / (np.abs(E - ex_o) + 1e-10)
         dets = H.pack(t64(basis))
         idx = fgk.BasisIndex(dets)
-        for n_pass_cap in (None, 16):      # 16 slots force the multi-pass path
-            ws = None if n_pass_cap is None else fgk.Pt2Workspace(max(16, len(cand_o) // 3), "cuda:0")
+        for n_pass_cap in (None, 16, "queue"):      # small capacity forces the multi-pass path
+            if n_pass_cap is None:
+                ws = None
+            elif n_pass_cap == 16:
+                ws = fgk.Pt2Workspace(max(16, len(cand_o) // 3), "cuda:0")
+            else:   # radix partition in front of the hash (queues + table regions), also multi-pass
+                ws = fgk.Pt2Workspace(max(4096, len(cand_o) // 2), "cuda:0", queue_pairs=max(64, raw // 3))
+                assert ws.partition["queue_bits"] >= 10
             cand, cpl, dg, imp, st = fgk.pt2_candidates(H, idx, torch.from_numpy(v).cuda(), E,
                                                         workspace=ws)
             assert st["raw_candidates"] == raw
@@ -529,7 +535,8 @@ def test_config5_shape_pt2_96_sites(fgk):
     imp_o = c64 ** 2 / (np.abs(E - O.diag(cand_o)) + 1e-10)
     dets = H.pack(t64(basis))
     idx = fgk.BasisIndex(dets)
-    for ws in (None, fgk.Pt2Workspace(len(cand_o) // 5, "cuda:0")):
+    for ws in (None, fgk.Pt2Workspace(len(cand_o) // 5, "cuda:0"),
+               fgk.Pt2Workspace(len(cand_o) // 2, "cuda:0", queue_pairs=raw // 2)):
         cand, cpl, dg, imp, st = fgk.pt2_candidates(H, idx, torch.from_numpy(v).cuda(), E, workspace=ws)
         assert st["raw_candidates"] == raw
         got = {bytes(r): i for i, r in enumerate(unpack_np(dets_np(cand), n_orb))}

@@ -25,9 +25,11 @@ perm = (torch.randperm(n, generator=torch.Generator().manual_seed(0))[:ns].cuda(
         else torch.arange(ns, device="cuda"))
 coeff[perm] = torch.exp(-torch.arange(ns, dtype=torch.float64, device="cuda") / (0.25 * ns))
 coeff /= torch.linalg.norm(coeff)
-from flow_guided_krylov_b200.expansion import default_pt2_capacity
+from flow_guided_krylov_b200.expansion import default_pt2_workspace
 ns = min(n_src, n)
-ws = fgk.Pt2Workspace(cap if cap else default_pt2_capacity(H, ns), "cuda:0")
+part = os.environ.get("FGK_PT2_PARTITION", "1") == "1"
+ws = fgk.Pt2Workspace(cap, "cuda:0") if cap else default_pt2_workspace(H, ns, partition=part)
+print("partition:", getattr(ws, "partition", None), "capacity", ws.capacity, flush=True)
 for rep in range(3):
     torch.cuda.synchronize(); t0 = time.time()
     sel, imp, st = fgk.pt2_select(H, idx, coeff, -60.0, 500, workspace=ws)
