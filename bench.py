@@ -468,7 +468,7 @@ def run_ours(args):
         coeff /= torch.linalg.norm(coeff)
         from flow_guided_krylov_b200.expansion import default_pt2_workspace
         n_local_src = -(-ns // world)      # a rank accumulates ~1/world of the candidates
-        wsp = default_pt2_workspace(H, n_local_src, partition=not args.pt2_direct)   # reused across sweeps
+        wsp = default_pt2_workspace(H, n_local_src, partition=args.pt2_partition)   # reused across sweeps
         reps = 3
         sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500, workspace=wsp)   # warm-up sweep
         barrier()
@@ -591,8 +591,8 @@ def main():
                     help="N>1: separate NCCL all-gather after the product instead of the fused peer-store kernel")
     ap.add_argument("--no-krylov", action="store_true", help="skip the Davidson / expm leg")
     ap.add_argument("--pt2-sources", type=int, default=2048)
-    ap.add_argument("--pt2-direct", action="store_true",
-                    help="PT2: upsert straight into the hash map (no radix partition in front)")
+    ap.add_argument("--pt2-partition", action="store_true",
+                    help="PT2: radix partition (queues by top hash bits) in front of the hash map")
     ap.add_argument("--conn-dets", type=int, default=1024, help="determinants of the connection-enumeration leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=256)

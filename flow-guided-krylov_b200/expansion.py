@@ -209,7 +209,7 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
     return tuple(torch.cat([o[i] for o in outs]) for i in range(4)) + (stats,)
 
 
-def default_pt2_capacity(ham, n_sources, partition=True):
+def default_pt2_capacity(ham, n_sources, partition=False):
     """distinct-candidate capacity for a sweep over n_sources determinants: every raw
     connection could be a distinct candidate; bounded by the free HBM.  Per unit of capacity:
     16 B table + 24 B pool + 24 B export buffers, plus 2 x 30 B of partition queue."""
@@ -219,7 +219,12 @@ def default_pt2_capacity(ham, n_sources, partition=True):
     return int(min(max(4096, 1.05 * n_sources * n_conn), 0.8 * free / per, 2 ** 31))
 
 
-def default_pt2_workspace(ham, n_sources, partition=True):
+def default_pt2_workspace(ham, n_sources, partition=False):
+    """partition=True puts the radix partition (fgk_pt2_set_partition) in front of the hash.
+    Measured on B200 (profiles/README.md): enumerate + append runs at 1.8e10 candidates/s, but the
+    queue-ordered fold is still bound by compulsory misses into the (sparse, over-provisioned)
+    tag table, so the two-phase sweep is no faster than the direct one (18 vs 13.4 ms on the
+    bench sweep); it stays available, off by default."""
     cap = default_pt2_capacity(ham, n_sources, partition)
     return Pt2Workspace(cap, ham.device, queue_pairs="auto" if partition else None)
 

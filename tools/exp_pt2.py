@@ -27,7 +27,7 @@ coeff[perm] = torch.exp(-torch.arange(ns, dtype=torch.float64, device="cuda") / 
 coeff /= torch.linalg.norm(coeff)
 from flow_guided_krylov_b200.expansion import default_pt2_workspace
 ns = min(n_src, n)
-part = os.environ.get("FGK_PT2_PARTITION", "1") == "1"
+part = os.environ.get("FGK_PT2_PARTITION", "0") == "1"
 ws = fgk.Pt2Workspace(cap, "cuda:0") if cap else default_pt2_workspace(H, ns, partition=part)
 print("partition:", getattr(ws, "partition", None), "capacity", ws.capacity, flush=True)
 for rep in range(3):
