@@ -34,6 +34,11 @@ struct HamView {
     const double* hdiag;  // h_pp
     const double* jks;    // 0.5*(J_pq+J_qp) - 0.5*(K_pq+K_qp)   (molecular.py:163-182, p!=q)
     const double* jab;    // J_pq = g[p,p,q,q]                   (molecular.py:171)
+    // nibble row-sum tables (may be null): nib_x[(p*nchunk + c)*16 + v] = sum of x[p][q] over the
+    // orbitals q whose bits are set in nibble value v of 4-bit chunk c of an occupation word
+    const double* nib_jk;
+    const double* nib_jab;
+    int nchunk;           // ceil(n_orb / 4)
 };
 
 FGK_HD int fgk_popc(u64 x)
@@ -224,9 +229,9 @@ FGK_HD bool bra_element(const HamView& H, fgk_det bra, const Excitation& x, Ld l
 }
 
 // FP64 diagonal <D|H|D> on the float32-rounded tables (molecular.py:133-184 in
-// bit form).  `ldd` abstracts the table read.
+// bit form).  `ldd` abstracts the table read.  Generic pair-loop form.
 template <class Ldd>
-FGK_HD double diag_element(const HamView& H, fgk_det d, Ldd ldd)
+FGK_HD double diag_element_loops(const HamView& H, fgk_det d, Ldd ldd)
 {
     const int n = H.n_orb;
     double e = H.e_nuc;
@@ -263,6 +268,43 @@ FGK_HD double diag_element(const HamView& H, fgk_det d, Ldd ldd)
         }
     }
     return e;
+}
+
+// Same quantity from nibble row-sum tables: the (J-K) matrix is symmetric with a zero diagonal
+// (J_pp = K_pp), so  sum_{p<q in S} jks[p][q] = 1/2 sum_{p in S} rowsum_p(S), and a row sum over
+// an occupation word is nchunk table reads (one per 4-bit nibble) instead of a bit loop.
+template <class Ldd>
+FGK_HD double nib_rowsum(const double* T, int nchunk, u64 w, Ldd ldd)
+{
+    double s = 0.0;
+    for (int c = 0; c < nchunk; c++) s += ldd(T + c * 16 + (int)((w >> (4 * c)) & 15ull));
+    return s;
+}
+
+template <class Ldd>
+FGK_HD double diag_element(const HamView& H, fgk_det d, Ldd ldd)
+{
+    if (!H.nib_jk) return diag_element_loops(H, d, ldd);
+    const int n = H.n_orb, nc = H.nchunk;
+    double e = H.e_nuc, same = 0.0;
+    u64 xa = d.a;
+    while (xa) {
+        int bp = 63 - fgk_clz(xa);
+        xa &= ~(1ull << bp);
+        int p = n - 1 - bp;
+        e += ldd(H.hdiag + p);
+        same += nib_rowsum(H.nib_jk + (size_t)p * nc * 16, nc, d.a, ldd);
+        e += nib_rowsum(H.nib_jab + (size_t)p * nc * 16, nc, d.b, ldd);
+    }
+    u64 xb = d.b;
+    while (xb) {
+        int bp = 63 - fgk_clz(xb);
+        xb &= ~(1ull << bp);
+        int p = n - 1 - bp;
+        e += ldd(H.hdiag + p);
+        same += nib_rowsum(H.nib_jk + (size_t)p * nc * 16, nc, d.b, ldd);
+    }
+    return e + 0.5 * same;
 }
 
 // ---- per-determinant enumeration context -------------------------------------

@@ -78,22 +78,30 @@ extern "C" int fgk_ham_create(const double* h1_host, const double* g_host, int n
     build_host_tables(h1_host, g_host, n_orb, T);
     fgk_ham* H = new fgk_ham();
     H->device = device;
-    // diagonal tables in ONE contiguous, 16-byte-granular buffer (a single TMA bulk copy
-    // stages it into shared memory): [h_pp padded to an even count][jks][jab]
+    // diagonal tables: h_pp + nibble row-sum tables in ONE contiguous, 16-byte-granular buffer
+    // (a single TMA bulk copy stages it into shared memory); plain (J-K) / J matrices kept for
+    // the pair-loop fallback when the nibble tables exceed shared memory (n_orb > 56)
     const size_t npad = ((size_t)n_orb + 1) & ~(size_t)1, n2 = (size_t)n_orb * n_orb;
-    std::vector<double> dt(npad + 2 * n2, 0.0);
+    const size_t nn = (size_t)n_orb * T.nchunk * 16;
+    std::vector<double> dt(npad + 2 * nn, 0.0), jk(2 * n2, 0.0);
     for (int p = 0; p < n_orb; p++) dt[p] = T.hdiag[p];
-    for (size_t i = 0; i < n2; i++) { dt[npad + i] = T.jks[i]; dt[npad + n2 + i] = T.jab[i]; }
+    for (size_t i = 0; i < nn; i++) { dt[npad + i] = T.nib_jk[i]; dt[npad + nn + i] = T.nib_jab[i]; }
+    for (size_t i = 0; i < n2; i++) { jk[i] = T.jks[i]; jk[n2 + i] = T.jab[i]; }
     int rc;
     if ((rc = upload(T.h1, &H->h1)) || (rc = upload(T.g, &H->g)) || (rc = upload(T.w, &H->w)) ||
-        (rc = upload(dt, &H->dtab))) {
+        (rc = upload(dt, &H->dtab)) || (rc = upload(jk, &H->jkab))) {
         delete H;
         return rc;
     }
-    H->dtab_bytes = (unsigned)(dt.size() * sizeof(double));
+    const size_t bytes = dt.size() * sizeof(double);
+    const bool nib_ok = bytes <= 208 * 1024;
+    H->dtab_bytes = nib_ok ? (unsigned)bytes : 0;
     H->v.n_orb = n_orb; H->v.n_alpha = n_alpha; H->v.n_beta = n_beta; H->v.e_nuc = e_nuc;
     H->v.h1 = H->h1; H->v.g = H->g; H->v.w = H->w;
-    H->v.hdiag = H->dtab; H->v.jks = H->dtab + npad; H->v.jab = H->dtab + npad + n2;
+    H->v.hdiag = H->dtab; H->v.jks = H->jkab; H->v.jab = H->jkab + n2;
+    H->v.nchunk = T.nchunk;
+    H->v.nib_jk = nib_ok ? H->dtab + npad : nullptr;
+    H->v.nib_jab = nib_ok ? H->dtab + npad + nn : nullptr;
     *out = H;
     return FGK_OK;
 }
@@ -103,7 +111,7 @@ extern "C" int fgk_ham_destroy(fgk_ham_t h)
     if (!h) return FGK_OK;
     cudaSetDevice(h->device);
     cudaFree(h->h1); cudaFree(h->g); cudaFree(h->w);
-    cudaFree(h->dtab);
+    cudaFree(h->dtab); cudaFree(h->jkab);
     delete h;
     return FGK_OK;
 }
@@ -193,24 +201,30 @@ extern "C" int fgk_unpack_i64(const uint64_t* dets, int64_t n, int n_orb, int64_
 }
 
 // ---- K2 diagonal -----------------------------------------------------------------------
-// one thread per determinant; the h_pp / (J-K) / J tables (n*(2n+1) doubles: 37 KB at 48
-// orbitals, 66 KB at 64) are staged in shared memory by one TMA bulk copy per CTA.
-__global__ void __launch_bounds__(256)
+// one thread per determinant; h_pp and the nibble row-sum tables (66 KB at 32 orbitals, 148 KB
+// at 48) are staged in shared memory by ONE TMA bulk copy per CTA; a row sum over an occupation
+// word is then ceil(n/4) independent shared-memory reads.  Above 56 orbitals the tables do not
+// fit and the pair-loop form reads the plain matrices through the read-only path.
+static const int DIAG_BLOCK = 1024;
+
+__global__ void __launch_bounds__(DIAG_BLOCK)
 k_diag(HamView H, unsigned tab_bytes, const fgk_det* __restrict__ dets, i64 n, double* __restrict__ out)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_mbar;
-    tma_stage_table(s_raw, H.hdiag, tab_bytes, &s_mbar);
-    const double* s_tab = reinterpret_cast<const double*>(s_raw);
-    HamView S = H;
-    S.hdiag = s_tab;
-    S.jks = s_tab + (H.jks - H.hdiag);
-    S.jab = s_tab + (H.jab - H.hdiag);
-    auto lds = [](const double* p) { return *p; };
+    if (tab_bytes) {
+        tma_stage_table(s_raw, H.hdiag, tab_bytes, &s_mbar);
+        const double* s_tab = reinterpret_cast<const double*>(s_raw);
+        const double* g0 = H.hdiag;
+        H.nib_jk = s_tab + (H.nib_jk - g0);
+        H.nib_jab = s_tab + (H.nib_jab - g0);
+        H.hdiag = s_tab;
+    }
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
         ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + j);
         fgk_det dd = {d.x, d.y};
-        out[j] = diag_element(S, dd, lds);
+        out[j] = tab_bytes ? diag_element(H, dd, [](const double* p) { return *p; })
+                           : diag_element(H, dd, [](const double* p) { return __ldg(p); });
     }
 }
 
@@ -223,10 +237,10 @@ extern "C" int fgk_diag(fgk_ham_t h, const uint64_t* dets, int64_t n, double* ou
     size_t smem = h->dtab_bytes;
     static bool attr_set[64] = {false};
     if (smem > 48 * 1024 && !attr_set[h->device & 63]) {
-        FGK_CUDA(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        FGK_CUDA(cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         attr_set[h->device & 63] = true;
     }
-    k_diag<<<grid_for(n, 256, h->device, 4), 256, smem, (cudaStream_t)stream>>>(
+    k_diag<<<grid_for(n, DIAG_BLOCK, h->device, 2), DIAG_BLOCK, smem, (cudaStream_t)stream>>>(
         h->v, h->dtab_bytes, (const fgk_det*)dets, n, out);
     FGK_LAUNCH_CHECK();
     return FGK_OK;

@@ -23,6 +23,7 @@ void* hc_ham_create(const double* h1, const double* g, int n_orb, int n_alpha, i
     H->V.n_orb = n_orb; H->V.n_alpha = n_alpha; H->V.n_beta = n_beta; H->V.e_nuc = e_nuc;
     H->V.h1 = H->T.h1.data(); H->V.g = H->T.g.data(); H->V.w = H->T.w.data();
     H->V.hdiag = H->T.hdiag.data(); H->V.jks = H->T.jks.data(); H->V.jab = H->T.jab.data();
+    H->V.nib_jk = H->T.nib_jk.data(); H->V.nib_jab = H->T.nib_jab.data(); H->V.nchunk = H->T.nchunk;
     return H;
 }
 void hc_ham_destroy(void* h) { delete (HcHam*)h; }
@@ -33,6 +34,16 @@ void hc_diag(void* h, const u64* dets, long n, double* out)
     for (long i = 0; i < n; i++) {
         fgk_det d = {dets[2 * i], dets[2 * i + 1]};
         out[i] = diag_element(H->V, d, ldd_host);
+    }
+}
+
+// the generic pair-loop diagonal (cross-check of the nibble-table form hc_diag uses)
+void hc_diag_loops(void* h, const u64* dets, long n, double* out)
+{
+    HcHam* H = (HcHam*)h;
+    for (long i = 0; i < n; i++) {
+        fgk_det d = {dets[2 * i], dets[2 * i + 1]};
+        out[i] = diag_element_loops(H->V, d, ldd_host);
     }
 }
 

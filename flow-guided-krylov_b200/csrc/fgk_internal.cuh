@@ -36,8 +36,9 @@ struct fgk_ham {
     int device;
     HamView v;          // device pointers
     float *h1, *g, *w;
-    double* dtab;       // [h_pp (padded to even)] [jks n*n] [jab n*n], contiguous: one TMA bulk copy
-    unsigned dtab_bytes;
+    double* dtab;       // [h_pp (padded to even)] [nibble (J-K) rows] [nibble J rows]: one TMA bulk copy
+    unsigned dtab_bytes;  // 0 when the nibble tables would not fit shared memory (n_orb > 56)
+    double* jkab;       // plain jks | jab (n*n each), for the pair-loop fallback
 };
 
 struct IndexView {

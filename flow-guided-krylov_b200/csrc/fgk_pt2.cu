@@ -205,23 +205,23 @@ k_pt2_aggregate(Pt2View W, int mode, i64 per_block)
 
 // live candidates are compacted to the front of the outputs (order is not
 // deterministic; every consumer treats them as a set); counters[3] = live count.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, double energy,
              fgk_det* __restrict__ out_dets, double* __restrict__ out_coupling,
              double* __restrict__ out_diag, double* __restrict__ out_importance)
 {
-    // diagonal tables staged in shared memory by one TMA bulk copy (as in k_diag)
+    // h_pp + nibble row-sum tables staged in shared memory by one TMA bulk copy (as in k_diag)
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_mbar;
-    if (have_h) {
+    const bool staged = have_h && tab_bytes;
+    if (staged) {
         tma_stage_table(s_raw, H.hdiag, tab_bytes, &s_mbar);
         const double* s_tab = reinterpret_cast<const double*>(s_raw);
         const double* g0 = H.hdiag;
-        H.jks = s_tab + (H.jks - g0);
-        H.jab = s_tab + (H.jab - g0);
+        H.nib_jk = s_tab + (H.nib_jk - g0);
+        H.nib_jab = s_tab + (H.nib_jab - g0);
         H.hdiag = s_tab;
     }
-    auto ldd = [](const double* p) { return *p; };
     const int lane = threadIdx.x & 31;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     const i64 rounds = (n_slots + stride - 1) / stride;
@@ -245,7 +245,8 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
         if (out_coupling) out_coupling[o] = cpl;
         if (have_h) {
             fgk_det dd = {d.x, d.y};
-            double ex = diag_element(H, dd, ldd);
+            double ex = staged ? diag_element(H, dd, [](const double* p) { return *p; })
+                               : diag_element(H, dd, [](const double* p) { return __ldg(p); });
             if (out_diag) out_diag[o] = ex;
             if (out_importance) out_importance[o] = cpl * cpl / (fabs(energy - ex) + 1e-10);   // :547-548
         }
@@ -422,13 +423,13 @@ extern "C" int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double
     const unsigned tab_bytes = h ? h->dtab_bytes : 0;
     static bool attr_set[64] = {false};
     if (tab_bytes > 48 * 1024 && !attr_set[ws->device & 63]) {
-        FGK_CUDA(cudaFuncSetAttribute(k_pt2_export, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        FGK_CUDA(cudaFuncSetAttribute(k_pt2_export, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         attr_set[ws->device & 63] = true;
     }
-    i64 need = (n_slots + 255) / 256, cap = (i64)fgk_sm_count(ws->device) * 4;
+    i64 need = (n_slots + 1023) / 1024, cap = (i64)fgk_sm_count(ws->device) * 2;
     cudaStream_t st = (cudaStream_t)stream;
     FGK_CUDA(cudaMemsetAsync(ws->v.counters + 3, 0, sizeof(unsigned long long), st));
-    k_pt2_export<<<(int)(need < cap ? need : cap), 256, tab_bytes, st>>>(
+    k_pt2_export<<<(int)(need < cap ? need : cap), 1024, tab_bytes, st>>>(
         hv, h != nullptr, tab_bytes, ws->v, n_slots, energy, (fgk_det*)out_dets, out_coupling, out_diag,
         out_importance);
     FGK_LAUNCH_CHECK();

@@ -10,6 +10,8 @@ struct HostTables {
     int n;
     std::vector<float> h1, g, w;          // float32 tables (molecular.py:68-69)
     std::vector<double> hdiag, jks, jab;  // FP64 diagonal tables built from the float32 values
+    int nchunk;
+    std::vector<double> nib_jk, nib_jab;  // nibble row-sum tables (n * nchunk * 16 each), see fgk_core.cuh
 };
 
 // h1_in (n,n), g_in (n,n,n,n) are the caller's FP64 integrals; the reference
@@ -43,4 +45,21 @@ inline void build_host_tables(const double* h1_in, const double* g_in, int n, Ho
             T.jab[(size_t)p * n + q] = Jpq;
         }
     }
+    // nibble row sums: chunk c covers bits 4c..4c+3 of an occupation word, bit b <-> orbital n-1-b
+    T.nchunk = (n + 3) / 4;
+    T.nib_jk.assign((size_t)n * T.nchunk * 16, 0.0);
+    T.nib_jab.assign((size_t)n * T.nchunk * 16, 0.0);
+    for (int p = 0; p < n; p++)
+        for (int c = 0; c < T.nchunk; c++)
+            for (int v = 0; v < 16; v++) {
+                double sjk = 0.0, sab = 0.0;
+                for (int b = 0; b < 4; b++) {
+                    int bit = 4 * c + b, q = n - 1 - bit;
+                    if (!(v & (1 << b)) || q < 0) continue;
+                    sjk += T.jks[(size_t)p * n + q];
+                    sab += T.jab[(size_t)p * n + q];
+                }
+                T.nib_jk[((size_t)p * T.nchunk + c) * 16 + v] = sjk;
+                T.nib_jab[((size_t)p * T.nchunk + c) * 16 + v] = sab;
+            }
 }

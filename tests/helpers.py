@@ -66,6 +66,7 @@ def hostcheck():
         L.hc_ham_create.argtypes = [vp, vp, ci, ci, ci, dbl]
         L.hc_ham_destroy.argtypes = [vp]
         L.hc_diag.argtypes = [vp, vp, i64, vp]
+        L.hc_diag_loops.argtypes = [vp, vp, i64, vp]
         L.hc_connections.restype = i64
         L.hc_connections.argtypes = [vp, u64, u64, vp, vp, i64]
         L.hc_bra_row.restype = i64

@@ -64,6 +64,9 @@ def test_diag_matches_oracle_1e9(name):
     out = np.zeros(len(pk))
     hostcheck().hc_diag(hc, _p(pk), len(pk), _p(out))
     assert np.abs(out - H.diag(g["dets"])).max() < 1e-9          # tolerance: 1e-9 Ha
+    out2 = np.zeros(len(pk))
+    hostcheck().hc_diag_loops(hc, _p(pk), len(pk), _p(out2))     # pair-loop form == nibble-table form
+    assert np.abs(out - out2).max() < 1e-11
     hostcheck().hc_ham_destroy(hc)
 
 
