@@ -270,3 +270,164 @@ extern "C" int fgk_spmv_sell_z(int64_t n_rows, const int64_t* slice_ptr, const i
 {
     return launch_spmv_sell<true>(n_rows, slice_ptr, sell_cols, sell_vals, x, y, device, stream);
 }
+
+// ======================================================================================
+// SELL-32 with exact-float32 off-diagonal storage ("packed" flavour).
+// Every off-diagonal element of the projected H is an exact float32 number (the reference
+// keeps float32 integrals: +-h_pq, +-g_pqrs, +-fp32(g - g); the symmetrised flavour too
+// whenever <i|H|j> = <j|H|i> or one of them is filtered), only the diagonal is a genuine
+// FP64 sum.  Storing {float v0, float v1, int c0, int c1} per lane per pair-column makes one
+// 16-byte load carry two nonzeros (8 B/nnz instead of 12) while the arithmetic stays FP64:
+// (double)v is exact, products and sums are the same FP64 operations on the same numbers.
+// The diagonal lives in its own FP64 array and is applied in the epilogue.
+// fgk_sell_pack_f32 refuses (flag) if any off-diagonal value is not float32-exact.
+// ======================================================================================
+__device__ __forceinline__ uint4 ld_stream_u32x4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <bool CPLX, int UNROLL>
+__global__ void __launch_bounds__(SELL_WARPS * 32)
+k_spmv_sell_f32(i64 n_rows, i64 row_offset, const i64* __restrict__ slice_ptr,
+                const uint4* __restrict__ packed, const double* __restrict__ diag,
+                const double* __restrict__ x, double* __restrict__ y)
+{
+    __shared__ double s_part[SELL_WARPS][32][CPLX ? 2 : 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const i64 s = blockIdx.x;
+    const i64 base = __ldg(slice_ptr + s);                 // in 16-byte units
+    const i64 npair = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const uint4* p0 = packed + base + lane;
+    Acc<CPLX> acc;
+    i64 k2 = w;
+    for (; k2 + (i64)SELL_WARPS * (UNROLL - 1) < npair; k2 += (i64)SELL_WARPS * UNROLL) {
+        uint4 q[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) q[u] = ld_stream_u32x4(p0 + (k2 + (i64)SELL_WARPS * u) * 32);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            acc.fma((double)__uint_as_float(q[u].x), x, (int)q[u].z);
+            acc.fma((double)__uint_as_float(q[u].y), x, (int)q[u].w);
+        }
+    }
+    for (; k2 < npair; k2 += SELL_WARPS) {
+        uint4 q = ld_stream_u32x4(p0 + k2 * 32);
+        acc.fma((double)__uint_as_float(q.x), x, (int)q.z);
+        acc.fma((double)__uint_as_float(q.y), x, (int)q.w);
+    }
+    s_part[w][lane][0] = acc.re;
+    if (CPLX) s_part[w][lane][CPLX ? 1 : 0] = Acc<CPLX>::imag(acc);
+    __syncthreads();
+    if (w == 0) {
+        const i64 r = s * 32 + lane;
+        if (r < n_rows) {
+            double re = 0.0, im = 0.0;
+#pragma unroll
+            for (int qd = 0; qd < SELL_WARPS; qd++) {
+                re += s_part[qd][lane][0];
+                if (CPLX) im += s_part[qd][lane][CPLX ? 1 : 0];
+            }
+            const double dg = __ldg(diag + r);
+            if (CPLX) {
+                double2 xr = __ldg(reinterpret_cast<const double2*>(x) + row_offset + r);
+                reinterpret_cast<double2*>(y)[r] = make_double2(fma(dg, xr.x, re), fma(dg, xr.y, im));
+            } else {
+                y[r] = fma(dg, __ldg(x + row_offset + r), re);
+            }
+        }
+    }
+}
+
+// CSR rows -> packed SELL-32.  The diagonal entry (column == row_offset + r) goes to diag[r];
+// slice_ptr (16-byte units) is sized by the caller from (row length - 1).  *inexact is set if an
+// off-diagonal value does not survive the float32 round trip.
+__global__ void __launch_bounds__(256)
+k_sell_pack_f32(i64 n_rows, i64 row_offset, const i64* __restrict__ row_ptr,
+                const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                const i64* __restrict__ slice_ptr, uint4* __restrict__ packed,
+                double* __restrict__ diag, int* inexact)
+{
+    const i64 s = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const i64 base = slice_ptr[s];
+    const i64 npair = (slice_ptr[s + 1] - base) >> 5;
+    const i64 r = s * 32 + lane;
+    i64 rs = 0, len = 0, dpos = -1;
+    if (r < n_rows) {
+        rs = row_ptr[r]; len = row_ptr[r + 1] - rs;
+        // position of the diagonal inside the row (first entry for unsorted rows; search otherwise)
+        for (i64 k = 0; k < len; k++)
+            if (cols[rs + k] == (int32_t)(row_offset + r)) { dpos = k; break; }
+        if (w == 0) diag[r] = dpos >= 0 ? vals[rs + dpos] : 0.0;
+    }
+    const i64 noff = dpos >= 0 ? len - 1 : len;           // off-diagonal entries of this row
+    bool bad = false;
+    for (i64 k2 = w; k2 < npair; k2 += nw) {
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        for (int h = 0; h < 2; h++) {
+            i64 k = 2 * k2 + h;                            // k-th off-diagonal entry
+            if (k < noff) {
+                i64 src = rs + (dpos >= 0 && k >= dpos ? k + 1 : k);
+                double v = vals[src];
+                float f = (float)v;
+                if ((double)f != v) bad = true;
+                if (h == 0) { q.x = __float_as_uint(f); q.z = (unsigned)cols[src]; }
+                else { q.y = __float_as_uint(f); q.w = (unsigned)cols[src]; }
+            }
+        }
+        packed[base + k2 * 32 + lane] = q;
+    }
+    if (bad) atomicExch(inexact, 1);
+}
+
+extern "C" int fgk_sell_pack_f32(int64_t n_rows, int64_t row_offset, const int64_t* row_ptr,
+                                 const int32_t* cols, const double* vals, const int64_t* slice_ptr,
+                                 void* packed, double* diag, int* inexact_flag, int device, void* stream)
+{
+    if (n_rows == 0) return FGK_OK;
+    if (!row_ptr || !cols || !vals || !slice_ptr || !packed || !diag || !inexact_flag || n_rows < 0)
+        return fgk_fail(FGK_ERR_ARG, "fgk_sell_pack_f32: bad argument");
+    if ((uintptr_t)packed & 15) return fgk_fail(FGK_ERR_ARG, "fgk_sell_pack_f32: packed must be 16-byte aligned");
+    FGK_CUDA(cudaSetDevice(device));
+    i64 n_slices = (n_rows + 31) / 32;
+    k_sell_pack_f32<<<(unsigned)n_slices, 256, 0, (cudaStream_t)stream>>>(
+        n_rows, row_offset, (const i64*)row_ptr, cols, vals, (const i64*)slice_ptr, (uint4*)packed, diag,
+        inexact_flag);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+template <bool CPLX>
+static int launch_spmv_sell_f32(int64_t n_rows, int64_t row_offset, const int64_t* slice_ptr,
+                                const void* packed, const double* diag, const double* x, double* y,
+                                int device, void* stream)
+{
+    if (n_rows == 0) return FGK_OK;
+    if (!slice_ptr || !packed || !diag || !x || !y || n_rows < 0)
+        return fgk_fail(FGK_ERR_ARG, "fgk_spmv_sell_f32: bad argument");
+    if ((uintptr_t)packed & 15) return fgk_fail(FGK_ERR_ARG, "fgk_spmv_sell_f32: packed must be 16-byte aligned");
+    FGK_CUDA(cudaSetDevice(device));
+    i64 n_slices = (n_rows + 31) / 32;
+    k_spmv_sell_f32<CPLX, 4><<<(unsigned)n_slices, SELL_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        n_rows, row_offset, (const i64*)slice_ptr, (const uint4*)packed, diag, x, y);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+extern "C" int fgk_spmv_sell_f32_f64(int64_t n_rows, int64_t row_offset, const int64_t* slice_ptr,
+                                     const void* packed, const double* diag, const double* x, double* y,
+                                     int device, void* stream)
+{
+    return launch_spmv_sell_f32<false>(n_rows, row_offset, slice_ptr, packed, diag, x, y, device, stream);
+}
+
+extern "C" int fgk_spmv_sell_f32_z(int64_t n_rows, int64_t row_offset, const int64_t* slice_ptr,
+                                   const void* packed, const double* diag, const double* x, double* y,
+                                   int device, void* stream)
+{
+    return launch_spmv_sell_f32<true>(n_rows, row_offset, slice_ptr, packed, diag, x, y, device, stream);
+}

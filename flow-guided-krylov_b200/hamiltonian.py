@@ -100,14 +100,62 @@ class ProjectedH:
             self.vals = self.vals[:0]
         return self
 
+    def to_sell_packed(self, keep_csr=True):
+        """SELL-32 with exact-float32 off-diagonal storage + FP64 diagonal (fgk_sell_pack_f32):
+        8 B per nonzero instead of 12, FP64 arithmetic on the same numbers (bit-identical
+        products).  Possible whenever every off-diagonal value is a float32 number -- always for
+        H_RAW, and for H_SYM when <i|H|j> = <j|H|i> (symmetric integrals).  Raises if not."""
+        if getattr(self, "_sellf", None) is not None:
+            return self
+        self._need_csr("to_sell_packed")
+        dev = self.cols.device
+        n_slices = (self.n_rows + 31) // 32
+        lens = torch.zeros(n_slices * 32, dtype=torch.int64, device=dev)
+        lens[: self.n_rows] = self.row_ptr[1:] - self.row_ptr[:-1]
+        width = (lens.view(n_slices, 32).max(dim=1).values + 1) // 2          # pair-columns per slice
+        slice_ptr = torch.zeros(n_slices + 1, dtype=torch.int64, device=dev)  # in 16-byte units
+        torch.cumsum(width * 32, 0, out=slice_ptr[1:])
+        total = int(slice_ptr[-1].item()) if n_slices else 0
+        packed = torch.empty(max(total, 1), 4, dtype=torch.int32, device=dev)
+        diag = torch.empty(self.n_rows, dtype=torch.float64, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.n_rows:
+            nat.check(nat.lib().fgk_sell_pack_f32(
+                self.n_rows, self.row_begin, nat.ptr(self.row_ptr, torch.int64),
+                nat.ptr(self.cols, torch.int32), nat.ptr(self.vals, torch.float64),
+                nat.ptr(slice_ptr, torch.int64), nat.ptr(packed), nat.ptr(diag, torch.float64),
+                nat.ptr(flag, torch.int32), nat.device_index(self.device), nat.stream_ptr(self.device)))
+        if int(flag.item()):
+            raise RuntimeError("to_sell_packed: some off-diagonal values are not float32-exact "
+                               "(non-symmetric integrals with H_SYM?); use to_sell()")
+        self._sellf = (slice_ptr, packed, diag)
+        self._nnz = self.nnz
+        if not keep_csr:
+            self._diag_cache = diag
+            self.cols = self.cols[:0]
+            self.vals = self.vals[:0]
+            self.sell_only = True
+        return self
+
     def matvec(self, x, out=None, fmt=None):
         """y = H[row_begin:row_end, :] @ x ; x real FP64 or complex128, length n.
-        Uses the SELL-32 copy when to_sell() was called (fmt='csr' forces the CSR kernel)."""
+        Uses the packed SELL-32 copy if to_sell_packed() was called, else the SELL-32 copy of
+        to_sell(), else CSR (fmt = 'packed' | 'sell' | 'csr' forces one)."""
         if x.shape[0] != self.n:
             raise ValueError(f"matvec: x has {x.shape[0]} entries, H has {self.n} columns")
         dev = nat.device_index(self.device)
+        sellf = getattr(self, "_sellf", None)
+        if sellf is not None and fmt in (None, "packed"):
+            cplx = x.is_complex()
+            x = x.to(torch.complex128 if cplx else torch.float64).contiguous()
+            y = out if out is not None else torch.empty(self.n_rows, dtype=x.dtype, device=x.device)
+            fn = nat.lib().fgk_spmv_sell_f32_z if cplx else nat.lib().fgk_spmv_sell_f32_f64
+            nat.check(fn(self.n_rows, self.row_begin, nat.ptr(sellf[0], torch.int64), nat.ptr(sellf[1]),
+                         nat.ptr(sellf[2], torch.float64), C.c_void_p(x.data_ptr()),
+                         C.c_void_p(y.data_ptr()), dev, nat.stream_ptr(self.device)))
+            return y
         sell = getattr(self, "_sell", None)
-        if sell is not None and fmt != "csr":
+        if sell is not None and fmt in (None, "sell", "packed"):
             cplx = x.is_complex()
             x = x.to(torch.complex128 if cplx else torch.float64).contiguous()
             y = out if out is not None else torch.empty(self.n_rows, dtype=x.dtype, device=x.device)

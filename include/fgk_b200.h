@@ -156,6 +156,23 @@ int fgk_spmv_sell_f64(int64_t n_rows, const int64_t* slice_ptr, const int32_t* s
 int fgk_spmv_sell_z(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
                     const double* sell_vals, const double* x, double* y, int device, void* stream);
 
+/* Packed SELL-32: exact-float32 off-diagonal values + FP64 diagonal (8 B per nonzero instead
+ * of 12; FP64 arithmetic on the same numbers, hence bit-identical products).  One 16-byte unit
+ * {float v0, float v1, int32 c0, int32 c1} per lane per pair-column; slice_ptr counts 16-byte
+ * units and is sized from (row length - 1) rounded up to even; the diagonal entry of row r
+ * (column row_offset + r) goes to diag[r].  *inexact_flag (device int, zeroed by the caller)
+ * is set if some off-diagonal value is not exactly representable in float32 -- then the
+ * packed copy must not be used. */
+int fgk_sell_pack_f32(int64_t n_rows, int64_t row_offset, const int64_t* row_ptr, const int32_t* cols,
+                      const double* vals, const int64_t* slice_ptr, void* packed, double* diag,
+                      int* inexact_flag, int device, void* stream);
+int fgk_spmv_sell_f32_f64(int64_t n_rows, int64_t row_offset, const int64_t* slice_ptr,
+                          const void* packed, const double* diag, const double* x, double* y,
+                          int device, void* stream);
+int fgk_spmv_sell_f32_z(int64_t n_rows, int64_t row_offset, const int64_t* slice_ptr,
+                        const void* packed, const double* diag, const double* x, double* y,
+                        int device, void* stream);
+
 /* ---- multi-GPU H.v with the all-gather fused into the product (one process per GPU) ----
  * fgk_peer_alloc: cudaMalloc'ed, zeroed buffer + its 64-byte cudaIpc handle (exchange the
  * handles with any host-side collective); fgk_peer_open maps a peer's buffer into this

@@ -219,7 +219,7 @@ def test_spmv_real_and_complex(fgk):
     np.cumsum(lens, out=rp[1:])
     mats.append((rp, rng.integers(0, 400, size=rp[-1]).astype(np.int32),
                  rng.standard_normal(rp[-1]), 400))
-    for indptr, indices, data, ncol in mats:
+    for mi, (indptr, indices, data, ncol) in enumerate(mats):
         P = fgk.ProjectedH(ncol, torch.from_numpy(indptr).cuda(), torch.from_numpy(indices).cuda(),
                            torch.from_numpy(data).cuda(), "cuda:0", 0, len(indptr) - 1)
         x = rng.standard_normal(ncol)
@@ -235,6 +235,16 @@ def test_spmv_real_and_complex(fgk):
         assert np.abs(ys - orc.csr_matvec(indptr, indices, data, x)).max() < 1e-12
         assert np.abs(yzs - orc.csr_matvec(indptr, indices, data, z)).max() < 1e-12
         assert np.array_equal(P.matvec(torch.from_numpy(x).cuda(), fmt="csr").cpu().numpy(), y)
+        # packed SELL-32 (float32-exact off-diagonals): the golden matrix qualifies, the random one does not
+        if mi == 0:
+            P.to_sell_packed()
+            yp = P.matvec(torch.from_numpy(x).cuda(), fmt="packed").cpu().numpy()
+            yzp = P.matvec(torch.from_numpy(z).cuda(), fmt="packed").cpu().numpy()
+            assert np.abs(yp - orc.csr_matvec(indptr, indices, data, x)).max() < 1e-12
+            assert np.abs(yzp - orc.csr_matvec(indptr, indices, data, z)).max() < 1e-12
+        else:
+            with pytest.raises(RuntimeError):
+                P.to_sell_packed()
 
 
 @pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide"])
@@ -476,6 +486,15 @@ def test_large_cas_window_properties(fgk):
     ycsr = P.matvec(x)
     P.to_sell()
     assert float((P.matvec(x) - ycsr).abs().max()) < 1e-10
+    # packed SELL-32 (8 B/nnz): bit-level agreement with the FP64-stored SELL product is not required
+    # (different summation tree), 1e-10 is
+    Pp = H.projected_csr(dets, fgk.H_RAW, packed=True, index=P._index).to_sell_packed()
+    assert float((Pp.matvec(x) - ycsr).abs().max()) < 1e-10
+    zz = torch.complex(x, y)
+    assert float((Pp.matvec(zz).real - ycsr).abs().max()) < 1e-10
+    Ps = H.projected_csr(dets, fgk.H_SYM, packed=True, index=P._index, row_begin=777, row_end=n - 5).to_sell_packed()
+    assert float((Ps.matvec(x) - S.matvec(x)[777:n - 5]).abs().max()) < 1e-10
+    del Pp, Ps
     # SELL-32 built directly by the fill kernel (no CSR): same operator, diagonal and size
     Q = H.projected_sell(dets, fgk.H_RAW, packed=True, index=P._index)
     assert Q.nnz == P.nnz and torch.equal(Q.row_ptr, P.row_ptr)
