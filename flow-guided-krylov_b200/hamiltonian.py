@@ -137,6 +137,16 @@ class ProjectedH:
             self.sell_only = True
         return self
 
+    def optimize_for_matvec(self, min_rows=16384):
+        """Pick the fastest storage for repeated H.v: packed SELL-32 when every off-diagonal is
+        float32-exact, else SELL-32; operators below `min_rows` rows stay on CSR (launch bound)."""
+        if self.n_rows < min_rows or getattr(self, "sell_only", False):
+            return self
+        try:
+            return self.to_sell_packed()
+        except RuntimeError:
+            return self.to_sell()
+
     def matvec(self, x, out=None, fmt=None):
         """y = H[row_begin:row_end, :] @ x ; x real FP64 or complex128, length n.
         Uses the packed SELL-32 copy if to_sell_packed() was called, else the SELL-32 copy of

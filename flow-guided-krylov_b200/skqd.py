@@ -109,6 +109,7 @@ class SampleBasedKrylovDiagonalization:
         if self._subspace_H is None:
             self._subspace_H = self.hamiltonian.projected_csr(
                 self._subspace_dets, nat.H_RAW, index=self._subspace_index, packed=True)
+            self._subspace_H.optimize_for_matvec()      # ~30 complex H.v per time step
         return self._subspace_H
 
     def _build_sparse_hamiltonian(self):

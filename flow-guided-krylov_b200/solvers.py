@@ -45,6 +45,8 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         return w[:k].clone(), v[:, :k].clone()
     diag = diagonal if diagonal is not None else P.diagonal()
     dev = diag.device
+    if matvec is None and hasattr(P, "optimize_for_matvec"):
+        P.optimize_for_matvec()                    # many products ahead: SELL-32 / packed storage
     nb = min(max(2 * k, k + 2), n)                 # initial block: lowest diagonal entries
     m_max = min(n, max_space if max_space is not None else max(12 * k, 36))
     m_max = max(m_max, nb + k)
