@@ -746,3 +746,40 @@ def test_random_shapes_on_device(fgk, seed):
         got = {bytes(r): i for i, r in enumerate(unpack_np(dets_np(cand), n_orb))}
         perm = np.array([got[bytes(r)] for r in cand_o])
         assert np.abs(cpl.cpu().numpy()[perm] - c64).max() < 1e-12
+
+
+def test_config5_shape_pt2_pass_invariance(fgk):
+    """BASELINE configs[4] shape (48 orbitals, 108,900-determinant CAS basis, 270,648 connections
+    per source) at 2,048 sources = 5.5e8 generated connections: the streamed selection must not
+    depend on how many bucket passes the workspace forces, and the counts must add up."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synth_integrals as bench_integrals, cas_window_basis
+    if torch.cuda.mem_get_info()[0] < 80e9:
+        pytest.skip("needs ~60 GB of free HBM")
+    n_orb = 48
+    h1, gg = bench_integrals(n_orb, 0)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, 24, n_orb, 12, 12), "cuda:0")
+    dets = torch.from_numpy(cas_window_basis(n_orb, 8, 11, 4).view(np.int64)).cuda()
+    n = dets.shape[0]
+    assert n == 108900
+    idx = fgk.BasisIndex(dets)
+    ns = 2048
+    coeff = torch.zeros(n, dtype=torch.float64, device="cuda")
+    pick = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:ns].cuda()
+    coeff[pick] = torch.exp(-torch.arange(ns, dtype=torch.float64, device="cuda") / (0.25 * ns))
+    sel1, imp1, st1 = fgk.pt2_select(H, idx, coeff, -60.0, 300)
+    ws = fgk.Pt2Workspace(st1["unique_candidates"] // 3, "cuda:0")
+    sel2, imp2, st2 = fgk.pt2_select(H, idx, coeff, -60.0, 300, workspace=ws)
+    assert st2["passes"] > st1["passes"]
+    # every source has 270,648 connections; 1,092 of them stay inside the CAS window (SURVEY 8d)
+    assert st1["raw_candidates"] == ns * 270648 and st2["raw_candidates"] == ns * 270648
+    assert st1["unique_candidates"] == st2["unique_candidates"]
+    assert torch.equal(sel1, sel2)
+    assert torch.allclose(imp1, imp2, rtol=1e-10, atol=0)
+    assert bool(torch.all(imp1[:-1] >= imp1[1:]))
+    # selected candidates are outside the basis and carry the right electron counts
+    assert bool(torch.all(idx.lookup(sel1) < 0))
+    cfg = H.unpack(sel1)
+    assert bool(torch.all(cfg[:, :n_orb].sum(1) == 12)) and bool(torch.all(cfg[:, n_orb:].sum(1) == 12))
