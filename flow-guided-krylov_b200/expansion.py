@@ -297,9 +297,32 @@ class SelectedCIExpander:
         self.device = getattr(hamiltonian, "device", "cpu")
         self.last_stats = {}
 
+    # Under torchrun (torch.distributed initialised, world > 1) the two heavy steps shard
+    # themselves: rows of the projected H by rank + fused H.v (dist.FusedShardedOperator) for
+    # bases above `sharded_min_rows`, and the PT2 sweep by candidate ownership
+    # (dist.pt2_select_sharded).  Every rank ends up with identical results.
+    sharded_min_rows = 65536
+
+    @staticmethod
+    def _world():
+        import torch.distributed as tdist
+        return tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
+
     # :408-443 -- float64, symmetrised; dense eigh for small n, Davidson above
     def _diagonalize_packed(self, dets):
         H = self.hamiltonian
+        n = dets.shape[0]
+        if self._world() > 1 and n >= self.sharded_min_rows:
+            from . import dist as fdist
+            index = BasisIndex(dets)
+            Pb, _ = fdist.build_sharded_h(H, dets, nat.H_SYM, index=index)
+            op = fdist.FusedShardedOperator(Pb)
+            try:
+                w, v = lowest_eigenpairs(op, k=1, matvec=op.matvec, diagonal=op.diagonal(), dense_max=0)
+                op.check()
+            finally:
+                op.close()
+            return float(w[0]), v[:, 0], index
         P = H.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)
         w, v = lowest_eigenpairs(P, k=1)
         return float(w[0]), v[:, 0], P._index
@@ -311,7 +334,11 @@ class SelectedCIExpander:
     # :451-554
     def _find_important_packed(self, dets, index, energy, v):
         H = self.hamiltonian
-        sel, imp, st = pt2_select(H, index, v, energy, self.config.max_configs_per_iter)
+        if self._world() > 1:
+            from . import dist as fdist
+            sel, imp, st = fdist.pt2_select_sharded(H, index, v, energy, self.config.max_configs_per_iter)
+        else:
+            sel, imp, st = pt2_select(H, index, v, energy, self.config.max_configs_per_iter)
         self.last_stats = st
         return sel, imp
 

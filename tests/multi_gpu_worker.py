@@ -93,6 +93,21 @@ def main():
     s_mx, r_mx, _ = fd.pt2_select_sharded(H, idx, coeff, 0.0, 40, mode=fgk.PT2_MAXABS)
     s_m1, r_m1, _ = fgk.pt2_select(H, idx, coeff, 0.0, 40, mode=fgk.PT2_MAXABS)
     assert torch.equal(s_mx, s_m1) and torch.equal(r_mx, r_m1)
+    # Stage 3 end to end under torchrun: sharded PT2 (and, above the row threshold, sharded H +
+    # fused H.v Davidson) must reproduce the single-process expander
+    ex = fgk.SelectedCIExpander(H, fgk.ResidualExpansionConfig(max_configs_per_iter=150))
+    b0 = H.unpack(dets[:600].contiguous())
+    ex.sharded_min_rows = 10 ** 9
+    b1, st1 = ex.expand_basis(b0)                       # sharded PT2 only
+    ex.sharded_min_rows = 64
+    b2, st2 = ex.expand_basis(b0)                       # + sharded H / fused Davidson
+    wsz = dist.get_world_size()
+    fgk.SelectedCIExpander._world = staticmethod(lambda: 1)
+    b3, st3 = fgk.SelectedCIExpander(H, fgk.ResidualExpansionConfig(max_configs_per_iter=150)).expand_basis(b0)
+    assert torch.equal(b1, b3) and torch.equal(b2, b3)
+    assert abs(st1["final_energy"] - st3["final_energy"]) < 1e-9
+    assert abs(st2["final_energy"] - st3["final_energy"]) < 1e-9
+    assert st3["configs_added"] == 150
     dist.barrier()
     if rank == 0:
         print(f"MULTI_GPU_OK world={world} n={n} nnz={Pfull.nnz} raw={st_ref['raw_candidates']}")
