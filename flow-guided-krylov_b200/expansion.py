@@ -141,16 +141,20 @@ def _key_sort_order(dets, n_orb):
     return o[torch.argsort(a[o], stable=True)]
 
 
-def select_top_k(dets, score, k, n_orb):
+def select_top_k(dets, score, k, n_orb, tie_eps=1e-9):
     """Deterministic top-k: score descending, ties by ascending key (the reference's
-    torch.topk leaves ties unspecified, residual_expansion.py:552)."""
+    torch.topk leaves ties unspecified, residual_expansion.py:552).  Scores within a
+    relative `tie_eps` of the k-th score count as tied with it: FP64 atomics accumulate in
+    arbitrary order, so exactly degenerate candidates (e.g. spin-flipped partners) differ in
+    the last bits from run to run -- the cut must not depend on that noise."""
     n = dets.shape[0]
     k = min(int(k), n)
     if k == 0:
         return dets[:0], score[:0]
     kth = torch.topk(score, k).values[-1]
-    sure = torch.nonzero(score > kth).squeeze(1)
-    tie = torch.nonzero(score == kth).squeeze(1)
+    band = tie_eps * kth.abs()
+    sure = torch.nonzero(score > kth + band).squeeze(1)
+    tie = torch.nonzero((score >= kth - band) & (score <= kth + band)).squeeze(1)
     need = k - sure.numel()
     if tie.numel() > need:
         tie = tie[_key_sort_order(dets[tie], n_orb)[:need]]

@@ -429,6 +429,47 @@ class MolecularHamiltonian:
         here: one launch, source-ascending order)."""
         return self.get_connections_batch(configs)
 
+    @torch.no_grad()
+    def local_energies(self, configs: torch.Tensor, log_amplitude, max_connections=8_000_000,
+                       nqs_chunk_size=16384) -> torch.Tensor:
+        """Stage-1 local energies E_loc(x) = <x|H|x> + sum_x' elem(x -> x') psi(x') / psi(x), the
+        quantity flows/physics_guided_training.py:335-457 assembles from
+        diagonal_elements_batch + get_connections(_parallel) + scatter_add -- here with bounded
+        memory: the batch is walked in groups whose connections (counted first with
+        fgk_conn_count) fit `max_connections`, connections stay packed until the amplitude
+        network needs them, and only `nqs_chunk_size` rows are unpacked at a time.
+        log_amplitude: callable (m, num_sites) float32 -> (m,) log psi (real or complex)."""
+        dets = self.pack(configs)
+        n = dets.shape[0]
+        out = self.diag_packed(dets).clone()
+        if n == 0:
+            return out
+        st = nat.stream_ptr(self.device)
+        counts = torch.empty(n, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().fgk_conn_count(self._h, nat.ptr(dets, torch.int64), n,
+                                           nat.ptr(counts, torch.int64), st))
+        csum = torch.cumsum(counts, 0).cpu()
+        log_psi0 = log_amplitude(configs.to(self.device).float()).clone()
+        off = torch.zeros(n, dtype=log_psi0.dtype if log_psi0.is_complex() else torch.float64,
+                          device=self.device)
+        lo = 0
+        while lo < n:
+            base = int(csum[lo - 1]) if lo else 0
+            hi = int(torch.searchsorted(csum, base + max_connections, right=True))
+            hi = max(hi, lo + 1)
+            od, el, src, _ = self.connections_packed(dets[lo:hi].contiguous())
+            m = od.shape[0]
+            if m:
+                lp = torch.empty(m, dtype=log_psi0.dtype, device=self.device)
+                for a in range(0, m, nqs_chunk_size):
+                    b = min(m, a + nqs_chunk_size)
+                    lp[a:b] = log_amplitude(self.unpack(od[a:b]).float())
+                ratio = torch.exp(lp - log_psi0[lo:hi][src])
+                off[lo:hi].index_add_(0, src, (el.to(torch.float64) * ratio).to(off.dtype))
+            lo = hi
+        res = out + off
+        return res.real if res.is_complex() else res
+
     # ---- projected Hamiltonian (K4 + K5) ---------------------------------------------------
     def projected_csr(self, basis, mode=nat.H_RAW, row_begin=0, row_end=None, sort_rows=False,
                       index: Optional[BasisIndex] = None, packed=False, profile=False) -> ProjectedH:

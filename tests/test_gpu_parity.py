@@ -783,3 +783,28 @@ def test_config5_shape_pt2_pass_invariance(fgk):
     assert bool(torch.all(idx.lookup(sel1) < 0))
     cfg = H.unpack(sel1)
     assert bool(torch.all(cfg[:, :n_orb].sum(1) == 12)) and bool(torch.all(cfg[:, n_orb:].sum(1) == 12))
+
+
+def test_local_energies_stage1(fgk):
+    """Stage-1 hook (physics_guided_training.py:335-457): chunked local energies against a direct
+    evaluation from the oracle's connections, for a real and a complex log-amplitude."""
+    g = load_golden("ham_n2")
+    H, O, n_orb = make_pair(fgk, g)
+    cfg = g["dets"]
+    rng = np.random.default_rng(0)
+    w = torch.from_numpy(rng.standard_normal(2 * n_orb) * 0.3).float().cuda()
+    w2 = torch.from_numpy(rng.standard_normal(2 * n_orb) * 0.2).float().cuda()
+    for cplx in (False, True):
+        def log_amp(x):
+            r = (x @ w).double()
+            return torch.complex(r, (x @ w2).double()) if cplx else r
+        ref = []
+        for j, d in enumerate(cfg):
+            oc, oe = O.connections(d)
+            la0 = log_amp(torch.from_numpy(d[None].astype(np.float32)).cuda())[0]
+            la = log_amp(torch.from_numpy(oc.astype(np.float32)).cuda())
+            e = O.diag(d[None])[0] + (torch.from_numpy(oe.astype(np.float64)).cuda() * torch.exp(la - la0)).sum()
+            ref.append(complex(e).real if cplx else float(e))
+        for max_conn in (8_000_000, 700):          # one group / many groups
+            got = H.local_energies(t64(cfg), log_amp, max_connections=max_conn, nqs_chunk_size=257)
+            assert np.abs(got.cpu().numpy() - np.array(ref)).max() < 1e-9
