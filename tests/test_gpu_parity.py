@@ -792,12 +792,12 @@ def test_local_energies_stage1(fgk):
     H, O, n_orb = make_pair(fgk, g)
     cfg = g["dets"]
     rng = np.random.default_rng(0)
-    w = torch.from_numpy(rng.standard_normal(2 * n_orb) * 0.3).float().cuda()
-    w2 = torch.from_numpy(rng.standard_normal(2 * n_orb) * 0.2).float().cuda()
+    w = torch.from_numpy(rng.standard_normal(2 * n_orb) * 0.3).cuda()      # FP64 "network": the check is
+    w2 = torch.from_numpy(rng.standard_normal(2 * n_orb) * 0.2).cuda()     # about the assembly, not about float32 GEMMs
     for cplx in (False, True):
         def log_amp(x):
-            r = (x @ w).double()
-            return torch.complex(r, (x @ w2).double()) if cplx else r
+            r = x.double() @ w
+            return torch.complex(r, x.double() @ w2) if cplx else r
         ref = []
         for j, d in enumerate(cfg):
             oc, oe = O.connections(d)
