@@ -9,7 +9,7 @@ All compute is hand-written sm_100a CUDA in csrc/ behind the C ABI of
 include/fgk_b200.h.  There is no CPU fallback: importing is cheap, but any call
 without the built library and a CUDA device raises.
 """
-from ._native import H_DROP_ZEROS, H_FLAT_WALK, H_RAW, H_SYM, PT2_MAXABS, PT2_SUM  # noqa: F401
+from ._native import H_DROP_ZEROS, H_FLAT_WALK, H_HASH_WALK, H_RAW, H_SYM, PT2_MAXABS, PT2_SUM  # noqa: F401
 from .hamiltonian import (BasisIndex, MolecularHamiltonian, MolecularIntegrals,  # noqa: F401
                           ProjectedH, sort_unique_dets)
 from .expansion import (Pt2Workspace, ResidualBasedExpander, ResidualExpansionConfig,  # noqa: F401

@@ -14,7 +14,7 @@ from .build import LIB
 _lib = None
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-H_RAW, H_SYM, H_DROP_ZEROS, H_FLAT_WALK = 0, 1, 2, 4
+H_RAW, H_SYM, H_DROP_ZEROS, H_FLAT_WALK, H_HASH_WALK = 0, 1, 2, 4, 8
 PT2_SUM, PT2_MAXABS = 0, 1
 
 vp, i64, ci, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
@@ -35,6 +35,7 @@ _SIGNATURES = {
     "fgk_index_destroy": (ci, [vp]),
     "fgk_index_lookup": (ci, [vp, vp, i64, vp, vp]),
     "fgk_index_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+    "fgk_index_layout": (ci, [vp, C.POINTER(ci)]),
     "fgk_projh_count": (ci, [vp, vp, i64, i64, ci, vp, vp]),
     "fgk_projh_fill": (ci, [vp, vp, i64, i64, ci, vp, vp, vp, vp]),
     "fgk_projh_fill_sell": (ci, [vp, vp, i64, i64, ci, vp, vp, vp, vp]),

@@ -77,6 +77,30 @@ k_set_compact(const u64* __restrict__ set, u64 size, u64* __restrict__ list, uns
     }
 }
 
+// ra[i] / rb[i] = rank of determinant i's alpha / beta string in the ascending distinct lists
+__global__ void __launch_bounds__(256)
+k_string_ranks(const fgk_det* __restrict__ dets, i64 n, const u64* __restrict__ alist, i64 na,
+               const u64* __restrict__ blist, i64 nb, int32_t* __restrict__ ra, int32_t* __restrict__ rb)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + i);
+        i64 lo = 0, hi = na;
+        while (lo < hi) { i64 mid = (lo + hi) >> 1; if (__ldg(alist + mid) < d.x) lo = mid + 1; else hi = mid; }
+        ra[i] = (int32_t)lo;
+        lo = 0; hi = nb;
+        while (lo < hi) { i64 mid = (lo + hi) >> 1; if (__ldg(blist + mid) < d.y) lo = mid + 1; else hi = mid; }
+        rb[i] = (int32_t)lo;
+    }
+}
+
+// duplicates resolve to the LAST index, like the hash table
+__global__ void __launch_bounds__(256)
+k_pair_fill(const int32_t* __restrict__ ra, const int32_t* __restrict__ rb, i64 n, i64 nb, int32_t* pair)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        atomicMax(pair + (i64)ra[i] * nb + rb[i], (int32_t)i);
+}
+
 __global__ void __launch_bounds__(256)
 k_index_lookup(IndexView I, const fgk_det* __restrict__ q, i64 m, int32_t* __restrict__ out)
 {
@@ -166,6 +190,27 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     }
     cudaFree(tmp);
     cudaFree(d_cnt);
+    // rank form: string ranks per determinant and, when the basis covers at least 1/16 of its
+    // alpha x beta string product (always for CAS-like / product bases), the dense pair table
+    // the rank-based projected-H builder reads instead of probing the hash table
+    I->ra = I->rb = I->pair = nullptr;
+    if (n > 0) {
+        FGK_CUDA(cudaMalloc((void**)&I->ra, (size_t)n * sizeof(int32_t)));
+        FGK_CUDA(cudaMalloc((void**)&I->rb, (size_t)n * sizeof(int32_t)));
+        k_string_ranks<<<grid1d(n, device), 256, 0, st>>>(d, n, I->alist, I->n_alpha_strings, I->blist,
+                                                          I->n_beta_strings, I->ra, I->rb);
+        FGK_LAUNCH_CHECK();
+        const i64 prod = I->n_alpha_strings * I->n_beta_strings;
+        const i64 lim = 16 * n > (1ll << 20) ? 16 * n : (1ll << 20);
+        if (prod <= lim && prod < (1ll << 31)) {
+            FGK_CUDA(cudaMalloc((void**)&I->pair, (size_t)prod * sizeof(int32_t)));
+            FGK_CUDA(cudaMemsetAsync(I->pair, 0xFF, (size_t)prod * sizeof(int32_t), st));
+            k_pair_fill<<<grid1d(n, device), 256, 0, st>>>(I->ra, I->rb, n, I->n_beta_strings, I->pair);
+            FGK_LAUNCH_CHECK();
+        }
+        FGK_CUDA(cudaStreamSynchronize(st));
+    }
+    I->v.ra = I->ra; I->v.rb = I->rb; I->v.pair = I->pair; I->v.n_bstr = I->n_beta_strings;
     I->v.dets = d; I->v.n = n;
     I->v.table = I->table; I->v.mask = tsize - 1;
     I->v.aset = I->aset; I->v.amask = asz - 1;
@@ -180,6 +225,7 @@ extern "C" int fgk_index_destroy(fgk_index_t idx)
     cudaSetDevice(idx->device);
     cudaFree(idx->table); cudaFree(idx->aset); cudaFree(idx->bset);
     cudaFree(idx->alist); cudaFree(idx->blist);
+    cudaFree(idx->ra); cudaFree(idx->rb); cudaFree(idx->pair);
     delete idx;
     return FGK_OK;
 }
@@ -204,5 +250,12 @@ extern "C" int fgk_index_info(fgk_index_t idx, int64_t* n_dets, int64_t* n_alpha
     if (n_dets) *n_dets = idx->v.n;
     if (n_alpha_strings) *n_alpha_strings = idx->n_alpha_strings;
     if (n_beta_strings) *n_beta_strings = idx->n_beta_strings;
+    return FGK_OK;
+}
+
+extern "C" int fgk_index_layout(fgk_index_t idx, int* dense_pairs)
+{
+    if (!idx) return fgk_fail(FGK_ERR_ARG, "fgk_index_layout: null handle");
+    if (dense_pairs) *dense_pairs = idx->pair ? 1 : 0;
     return FGK_OK;
 }

@@ -50,14 +50,23 @@ struct IndexView {
     u64 amask;
     const u64* bset;
     u64 bmask;
+    // rank form of the basis (null for an empty basis): ra[i] / rb[i] = position of determinant
+    // i's alpha / beta string in the sorted distinct-string lists; pair[ra * n_bstr + rb] = basis
+    // index of that (alpha, beta) combination or -1 -- present only when the basis fills its
+    // string product densely enough (see fgk_index_create), else null.
+    const int32_t* ra;
+    const int32_t* rb;
+    const int32_t* pair;
+    i64 n_bstr;
 };
 
 struct fgk_index {
     int device;
     IndexView v;
     u64 *table, *aset, *bset;
-    u64 *alist, *blist;             // the distinct alpha / beta strings, compact
+    u64 *alist, *blist;             // the distinct alpha / beta strings, ascending
     i64 n_alpha_strings, n_beta_strings;
+    int32_t *ra, *rb, *pair;        // string ranks per determinant; dense pair table (may be null)
 };
 
 struct Pt2View {

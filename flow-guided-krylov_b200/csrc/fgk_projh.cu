@@ -259,6 +259,216 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
     }
 }
 
+
+// ---- rank-based row builder --------------------------------------------------------------
+// Same structure as k_projh2 (string lists drive the loops) but nothing is hashed and nothing
+// is decoded twice.  ncu on k_projh2 (profiles/r01h): a third of its instructions and over
+// half of its stall samples sit in the 128-bit hash probe, another eighth in 64-bit (n,n,n,n)
+// index arithmetic.  Here
+//   * a connected string is found by scanning the sorted distinct-string list, so its RANK is
+//     known; the column of (alpha rank, beta rank) is one 4-byte load from the dense pair
+//     table of the index (or, for sparse bases, one probe with the strings read back from
+//     the lists);
+//   * for alpha-beta doubles both the table offset and the sign parity split into an alpha
+//     part and a beta part: g[(e0 n + h0) n^2 + (e1 n + h1)], parity = par_a ^ par_b ^ 1
+//     (exc_parity_ket, class 4); the parts are computed once per single excitation and kept
+//     in shared memory, and the product loop runs flat over n_a * n_b with full lanes;
+//   * same-spin doubles met during the scan are queued (ring of 64 ranks per warp) and
+//     evaluated 32 at a time, instead of at the scan's lane occupancy (27 % on config 4).
+// Requires the scan mode for both spins (fewer distinct strings than same-spin excitations
+// per row); otherwise fgk_projh_* fall back to k_projh2.
+struct __align__(8) SEntry {
+    unsigned short he;     // hole << 8 | particle
+    unsigned short par;    // bit0 pk, bit1 pb (alpha-beta factors), bit2 s1 ket, bit3 s1 bra
+    int rank;              // rank of the target string
+};
+
+template <bool FILL, bool DENSE>
+__global__ void __launch_bounds__(FGK_BLOCK)
+k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_end, int mode,
+         i64* __restrict__ counts, const i64* __restrict__ row_ptr, const i64* __restrict__ slice_ptr,
+         int32_t* __restrict__ cols, double* __restrict__ vals)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    SEntry* const s_single = reinterpret_cast<SEntry*>(s_dyn) + (size_t)wib * 2 * cap;
+    int* const s_queue = reinterpret_cast<int*>(s_dyn + sizeof(SEntry) * 2 * (size_t)cap * FGK_WARPS_PER_BLOCK) + wib * 64;
+    const unsigned lt = (1u << lane) - 1u;
+    const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
+    const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
+    const bool sym = (mode & FGK_H_SYM) != 0, drop0 = (mode & FGK_H_DROP_ZEROS) != 0;
+    const bool need_sign = FILL || drop0;
+    const int n = H.n_orb, n2 = n * n;
+    const int nbs = (int)I.n_bstr;
+    LdgD ldd;
+    for (i64 i = row_begin + warp0; i < row_end; i += nwarps) {
+        const ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + i);
+        const fgk_det d = {dv.x, dv.y};
+        const int ia = __ldg(I.ra + i), ib = __ldg(I.rb + i);
+        const i64 rl = i - row_begin;
+        const i64 row_base = !FILL ? 0 : (slice_ptr ? __ldg(slice_ptr + (rl >> 5)) + 2 * (rl & 31)
+                                                    : __ldg(row_ptr + rl));
+        auto at = [&](i64 k) -> i64 {
+            return slice_ptr ? row_base + (k >> 1) * 64 + (k & 1) : row_base + k;
+        };
+        i64 pos = 0;
+        if (FILL && lane == 0) {
+            cols[at(0)] = (int32_t)i;
+            vals[at(0)] = diag_element(H, d, ldd);
+        }
+        pos += 1;
+        // column of (alpha rank, beta rank), or -1
+        auto column = [&](int ra2, int rb2) -> int {
+            if (DENSE) return __ldg(I.pair + (i64)ra2 * nbs + rb2);
+            fgk_det o = {__ldg(PL.alist + ra2), __ldg(PL.blist + rb2)};
+            return index_find(I, o);
+        };
+        // rb_ = table value seen from the ket j (gives <i|H|j>), rk = seen from the ket i
+        auto emit = [&](bool valid, int j, float rb_, float rk, int parb, int park) {
+            double v = 0.0;
+            bool keep = false;
+            if (valid) {
+                const bool kij = fabsf(rb_) > 1e-12f;
+                const bool kji = sym && fabsf(rk) > 1e-12f;
+                keep = kij || kji;
+                if (keep && need_sign) {
+                    const float vij = kij ? (parb ? -rb_ : rb_) : 0.f;
+                    const float vji = kji ? (park ? -rk : rk) : 0.f;
+                    v = sym ? 0.5 * ((double)vij + (double)vji) : (double)vij;
+                    if (drop0 && v == 0.0) keep = false;
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (FILL && keep) {
+                const i64 o = at(pos + __popc(b & lt));
+                cols[o] = j;
+                vals[o] = v;
+            }
+            pos += __popc(b);
+        };
+        int n_single[2] = {0, 0};
+#pragma unroll 1
+        for (int spin = 0; spin < 2; spin++) {
+            const u64 w = spin ? d.b : d.a;
+            const u64* list = spin ? PL.blist : PL.alist;
+            const int nl = (int)(spin ? PL.nb : PL.na);
+            SEntry* L = s_single + spin * cap;
+            int cnt = 0, qh = 0, qn = 0;
+            // evaluate m (<= 32) queued same-spin doubles, one per lane
+            auto flush = [&](int m) {
+                const bool valid0 = lane < m;
+                int j = -1;
+                float rb_ = 0.f, rk = 0.f;
+                int parb = 0, park = 0;
+                if (valid0) {
+                    const int t = s_queue[(qh + lane) & 63];
+                    j = spin ? column(ia, t) : column(t, ib);
+                    if (j >= 0) {
+                        const u64 w2 = __ldg(list + t);
+                        int h0, h1, e0, e1;
+                        double_from_strings(w, w2, n, h0, h1, e0, e1);
+                        rb_ = __ldg(H.w + ((h0 * n + e0) * n + h1) * n + e1);
+                        if (sym) rk = __ldg(H.w + ((e0 * n + h0) * n + e1) * n + h1);
+                        if (need_sign) {
+                            Excitation x, rx;
+                            x.cls = rx.cls = 2;       // the same-spin parity only reads the changed word
+                            x.h0 = h0; x.h1 = h1; x.e0 = e0; x.e1 = e1;
+                            rx.h0 = e0; rx.h1 = e1; rx.e0 = h0; rx.e1 = h1;
+                            const fgk_det kd = {w, 0}, ko = {w2, 0};
+                            park = exc_parity_ket(kd, n, x);
+                            parb = exc_parity_ket(ko, n, rx);
+                        }
+                    }
+                }
+                emit(j >= 0, j, rb_, rk, parb, park);
+            };
+            for (int t0 = 0; t0 < nl; t0 += 32) {
+                const int t = t0 + lane;
+                const u64 w2 = t < nl ? __ldg(list + t) : w;
+                const int pc = __popcll(w2 ^ w);
+                const unsigned bs = __ballot_sync(0xffffffffu, pc == 2);
+                if (pc == 2) {
+                    int hh, ee;
+                    single_from_strings(w, w2, n, hh, ee);
+                    const int pk = (__popcll(w & span_mask(n, ee, hh)) + (ee < hh)) & 1;
+                    const int pb = (__popcll(w2 & span_mask(n, hh, ee)) + (hh < ee)) & 1;
+                    const int sk = sign1_parity(w, n, ee, hh), sb = sign1_parity(w2, n, hh, ee);
+                    const int o = cnt + __popc(bs & lt);
+                    if (o < cap) {
+                        SEntry e;
+                        e.he = (unsigned short)((hh << 8) | ee);
+                        e.par = (unsigned short)(pk | (pb << 1) | (sk << 2) | (sb << 3));
+                        e.rank = t;
+                        L[o] = e;
+                    }
+                }
+                cnt += __popc(bs);
+                const unsigned bd = __ballot_sync(0xffffffffu, pc == 4);
+                if (bd) {
+                    if (pc == 4) s_queue[(qh + qn + __popc(bd & lt)) & 63] = t;
+                    qn += __popc(bd);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        flush(32);
+                        qh = (qh + 32) & 63;
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+            if (qn > 0) { flush(qn); __syncwarp(); }
+            n_single[spin] = cnt < cap ? cnt : cap;
+        }
+        __syncwarp();
+        // singles: column = (target rank, own rank of the other spin)
+#pragma unroll 1
+        for (int spin = 0; spin < 2; spin++) {
+            const SEntry* L = s_single + spin * cap;
+            for (int t0 = 0; t0 < n_single[spin]; t0 += 32) {
+                const int t = t0 + lane;
+                int j = -1, parb = 0, park = 0;
+                float rb_ = 0.f, rk = 0.f;
+                if (t < n_single[spin]) {
+                    const SEntry e = L[t];
+                    j = spin ? column(ia, e.rank) : column(e.rank, ib);
+                    if (j >= 0) {
+                        const int hh = e.he >> 8, ee = e.he & 0xff;
+                        rb_ = __ldg(H.h1 + hh * n + ee);
+                        if (sym) rk = __ldg(H.h1 + ee * n + hh);
+                        park = (e.par >> 2) & 1;
+                        parb = (e.par >> 3) & 1;
+                    }
+                }
+                emit(j >= 0, j, rb_, rk, parb, park);
+            }
+        }
+        // alpha-beta doubles: flat product of the two singles lists
+        const int nsa = n_single[0], nsb = n_single[1], total = nsa * nsb;
+        const SEntry* La = s_single;
+        const SEntry* Lb = s_single + cap;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            int j = -1, parb = 0, park = 0;
+            float rb_ = 0.f, rk = 0.f;
+            if (t < total) {
+                const int ka = t / nsb, kb = t - ka * nsb;
+                const SEntry ea = La[ka], eb = Lb[kb];
+                j = column(ea.rank, eb.rank);
+                if (j >= 0) {
+                    const int h0 = ea.he >> 8, e0 = ea.he & 0xff, h1 = eb.he >> 8, e1 = eb.he & 0xff;
+                    rb_ = __ldg(H.g + (h0 * n + e0) * n2 + h1 * n + e1);
+                    if (sym) rk = __ldg(H.g + (e0 * n + h0) * n2 + e1 * n + h1);
+                    park = (ea.par ^ eb.par ^ 1) & 1;
+                    parb = ((ea.par ^ eb.par) >> 1 ^ 1) & 1;
+                }
+            }
+            emit(j >= 0, j, rb_, rk, parb, park);
+        }
+        if (!FILL && lane == 0) counts[i - row_begin] = pos;
+        __syncwarp();
+    }
+}
+
 static int grid_rows(i64 rows, int device)
 {
     i64 need = (rows + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
@@ -282,6 +492,39 @@ static ProjLists proj_lists(fgk_ham_t h, fgk_index_t idx)
     return P;
 }
 
+
+// rank-based builder: usable when both spins are in scan mode and the index has its rank form
+static bool use_rank_builder(fgk_ham_t h, fgk_index_t idx, int mode, const ProjLists& P)
+{
+    if (mode & (FGK_H_FLAT_WALK | FGK_H_HASH_WALK)) return false;
+    return P.scan_a && P.scan_b && idx->ra != nullptr && idx->rb != nullptr;
+}
+
+template <bool FILL>
+static int launch_projh3(fgk_ham_t h, fgk_index_t idx, const ProjLists& P, i64 row_begin, i64 row_end,
+                         int mode, i64* counts, const i64* row_ptr, const i64* slice_ptr, int32_t* cols,
+                         double* vals, cudaStream_t st)
+{
+    const int n = h->v.n_orb, na = h->v.n_alpha, nb = h->v.n_beta;
+    int cap = na * (n - na) > nb * (n - nb) ? na * (n - na) : nb * (n - nb);
+    if (cap < 1) cap = 1;
+    const size_t smem = sizeof(SEntry) * 2 * (size_t)cap * FGK_WARPS_PER_BLOCK + 64 * sizeof(int) * FGK_WARPS_PER_BLOCK;
+    const int grid = grid_rows(row_end - row_begin, h->device);
+    if (idx->pair) {
+        if (smem > 48 * 1024)
+            FGK_CUDA(cudaFuncSetAttribute(k_projh3<FILL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_projh3<FILL, true><<<grid, FGK_BLOCK, smem, st>>>(h->v, idx->v, P, cap, row_begin, row_end, mode,
+                                                            counts, row_ptr, slice_ptr, cols, vals);
+    } else {
+        if (smem > 48 * 1024)
+            FGK_CUDA(cudaFuncSetAttribute(k_projh3<FILL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_projh3<FILL, false><<<grid, FGK_BLOCK, smem, st>>>(h->v, idx->v, P, cap, row_begin, row_end, mode,
+                                                             counts, row_ptr, slice_ptr, cols, vals);
+    }
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
 extern "C" int fgk_projh_count(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end,
                                int mode, int64_t* counts, void* stream)
 {
@@ -292,6 +535,10 @@ extern "C" int fgk_projh_count(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, 
     if (!counts) return fgk_fail(FGK_ERR_ARG, "fgk_projh_count: null counts");
     if (h->device != idx->device) return fgk_fail(FGK_ERR_ARG, "fgk_projh_count: device mismatch");
     FGK_CUDA(cudaSetDevice(h->device));
+    const ProjLists PLs = proj_lists(h, idx);
+    if (use_rank_builder(h, idx, mode, PLs))
+        return launch_projh3<false>(h, idx, PLs, row_begin, row_end, mode, (i64*)counts, nullptr, nullptr,
+                                    nullptr, nullptr, (cudaStream_t)stream);
     if (mode & FGK_H_FLAT_WALK)
         k_projh<false><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
             h->v, idx->v, row_begin, row_end, mode, (i64*)counts, nullptr, nullptr, nullptr);
@@ -314,6 +561,10 @@ extern "C" int fgk_projh_fill(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, i
     if (!row_ptr || !cols || !vals) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill: null pointer");
     if (h->device != idx->device) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill: device mismatch");
     FGK_CUDA(cudaSetDevice(h->device));
+    const ProjLists PLs = proj_lists(h, idx);
+    if (use_rank_builder(h, idx, mode, PLs))
+        return launch_projh3<true>(h, idx, PLs, row_begin, row_end, mode, nullptr, (const i64*)row_ptr, nullptr,
+                                   cols, vals, (cudaStream_t)stream);
     if (mode & FGK_H_FLAT_WALK)
         k_projh<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
             h->v, idx->v, row_begin, row_end, mode, nullptr, (const i64*)row_ptr, cols, vals);
@@ -339,8 +590,12 @@ extern "C" int fgk_projh_fill_sell(fgk_ham_t h, fgk_index_t idx, int64_t row_beg
     if (mode & FGK_H_FLAT_WALK) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_projh_fill_sell: not with FLAT_WALK");
     if (h->device != idx->device) return fgk_fail(FGK_ERR_ARG, "fgk_projh_fill_sell: device mismatch");
     FGK_CUDA(cudaSetDevice(h->device));
+    const ProjLists PLs = proj_lists(h, idx);
+    if (use_rank_builder(h, idx, mode, PLs))
+        return launch_projh3<true>(h, idx, PLs, row_begin, row_end, mode, nullptr, nullptr,
+                                   (const i64*)slice_ptr, sell_cols, sell_vals, (cudaStream_t)stream);
     k_projh2<true><<<grid_rows(row_end - row_begin, h->device), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, idx->v, proj_lists(h, idx), row_begin, row_end, mode, nullptr, nullptr,
+        h->v, idx->v, PLs, row_begin, row_end, mode, nullptr, nullptr,
         (const i64*)slice_ptr, sell_cols, sell_vals);
     FGK_LAUNCH_CHECK();
     return FGK_OK;

@@ -282,7 +282,10 @@ class BasisIndex:
     def info(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         nat.check(nat.lib().fgk_index_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return dict(n_dets=a.value, n_alpha_strings=b.value, n_beta_strings=c.value)
+        dense = C.c_int(0)
+        nat.check(nat.lib().fgk_index_layout(self._h, C.byref(dense)))
+        return dict(n_dets=a.value, n_alpha_strings=b.value, n_beta_strings=c.value,
+                    dense_pairs=bool(dense.value))
 
 
 def sort_unique_dets(dets, n_orb):

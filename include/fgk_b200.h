@@ -53,6 +53,11 @@ extern "C" {
 #define FGK_H_FLAT_WALK 4  /* OR-able: build rows by the flat reference-order walk  */
                            /*  over every excitation instead of the string-set      */
                            /*  driven builder (same entries; cross-check / debug)   */
+#define FGK_H_HASH_WALK 8  /* OR-able: string-set driven builder with a hash probe  */
+                           /*  per candidate, instead of the rank-based builder     */
+                           /*  (same entries; cross-check, and the automatic path   */
+                           /*  when a basis has more distinct strings than a row    */
+                           /*  has same-spin excitations)                           */
 
 /* PT2 accumulation flavours */
 #define FGK_PT2_SUM 0      /* signed coupling sum   (residual_expansion.py:515-520) */
@@ -112,6 +117,10 @@ int fgk_index_destroy(fgk_index_t idx);
 int fgk_index_lookup(fgk_index_t idx, const uint64_t* query, int64_t m, int32_t* out_idx, void* stream);
 /* number of distinct alpha / beta strings of the basis (host outputs) */
 int fgk_index_info(fgk_index_t idx, int64_t* n_dets, int64_t* n_alpha_strings, int64_t* n_beta_strings);
+/* *dense_pairs (host) = 1 if the index also holds the dense (alpha rank, beta rank) -> position
+ * table, which it builds when the basis covers at least 1/16 of its alpha x beta string product
+ * (or that product is below 2^20); the projected-H builder then needs no hash probe at all. */
+int fgk_index_layout(fgk_index_t idx, int* dense_pairs);
 
 /* ---- K5 projected Hamiltonian (CSR rows) ------------------------------------------
  * replaces matrix_elements_fast (molecular.py:471-516), get_sparse_matrix_elements

@@ -160,11 +160,13 @@ def test_projected_h(fgk, name):
     pat = np.zeros((n, n), bool)
     pat[np.repeat(np.arange(n), np.diff(M.indptr)), M.indices] = True
     assert np.array_equal(pat & off, (S != 0) & off)
-    # the string-set driven builder (default) and the flat reference-order walk agree entry by entry
+    # the rank-based builder (default), the hash-probing string-set builder and the flat
+    # reference-order walk agree entry by entry
     for mode in (fgk.H_RAW, fgk.H_SYM, fgk.H_SYM | fgk.H_DROP_ZEROS):
         A = H.projected_csr(basis, mode, sort_rows=True)
-        B = H.projected_csr(basis, mode | fgk.H_FLAT_WALK, sort_rows=True)
-        assert torch.equal(A.row_ptr, B.row_ptr) and torch.equal(A.cols, B.cols) and torch.equal(A.vals, B.vals)
+        for flag in (fgk.H_FLAT_WALK, fgk.H_HASH_WALK):
+            B = H.projected_csr(basis, mode | flag, sort_rows=True)
+            assert torch.equal(A.row_ptr, B.row_ptr) and torch.equal(A.cols, B.cols) and torch.equal(A.vals, B.vals)
     # row blocks reproduce the full build
     if n > 4:
         Pf = H.projected_csr(basis, fgk.H_RAW).to_scipy().toarray()
@@ -479,9 +481,15 @@ def test_large_cas_window_properties(fgk):
     a = float(torch.dot(y, S.matvec(x)))
     b = float(torch.dot(S.matvec(y), x))
     assert abs(a - b) < 1e-9 * max(1.0, abs(a))
-    F = H.projected_csr(dets, fgk.H_RAW | fgk.H_FLAT_WALK, packed=True, index=P._index, sort_rows=True)
-    assert torch.equal(F.row_ptr, P.row_ptr) and torch.equal(F.cols, P.cols) and torch.equal(F.vals, P.vals)
-    del F
+    assert P._index.info()["dense_pairs"]          # product basis: rank-based builder, no hash probes
+    for flag in (fgk.H_FLAT_WALK, fgk.H_HASH_WALK):
+        F = H.projected_csr(dets, fgk.H_RAW | flag, packed=True, index=P._index, sort_rows=True)
+        assert torch.equal(F.row_ptr, P.row_ptr) and torch.equal(F.cols, P.cols) and torch.equal(F.vals, P.vals)
+        del F
+    S2 = H.projected_csr(dets, fgk.H_SYM | fgk.H_HASH_WALK, packed=True, index=P._index, sort_rows=True)
+    S.sort_rows()
+    assert torch.equal(S2.row_ptr, S.row_ptr) and torch.equal(S2.cols, S.cols) and torch.equal(S2.vals, S.vals)
+    del S2
     # SELL-32 copy: same operator
     ycsr = P.matvec(x)
     P.to_sell()
@@ -524,6 +532,47 @@ def test_large_cas_window_properties(fgk):
             if i is not None:
                 assert col[i] == float(e)
         assert abs(col[j] - O.diag(cfg[j:j + 1])[0]) < TOL
+
+
+def test_rank_builder_without_dense_pair_table(fgk):
+    """A basis that covers < 1/16 of its alpha x beta string product (and more than 2^20 pairs):
+    the rank-based projected-H builder then reads the strings back from the sorted lists and probes
+    the hash table.  Must equal the hash-walk and the flat reference-order builders entry by entry,
+    also for a row block and for the SELL-32 direct fill."""
+    from itertools import combinations
+    from helpers import synth_integrals
+    n_orb, na, nb, n_act, n_froz = 32, 8, 8, 15, 4
+    h1, gg = synth_integrals(n_orb, seed=5)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, na + nb, n_orb, na, nb), "cuda:0")
+    strings = []
+    for occ in combinations(range(n_froz, n_froz + n_act), na - n_froz):
+        w = 0
+        for p in list(range(n_froz)) + list(occ):
+            w |= 1 << (n_orb - 1 - p)
+        strings.append(w)
+    s = np.array(sorted(strings), dtype=np.uint64)          # 1,365 strings, product 1.86e6 > 2^20
+    rng = np.random.default_rng(7)
+    pick = np.unique(rng.integers(0, len(s) ** 2, size=40000))
+    dnp = np.stack([s[pick // len(s)], s[pick % len(s)]], axis=1)
+    dets = torch.from_numpy(dnp.view(np.int64)).cuda()
+    n = dets.shape[0]
+    idx = fgk.BasisIndex(dets)
+    info = idx.info()
+    assert not info["dense_pairs"] and info["n_alpha_strings"] <= len(s)
+    for mode in (fgk.H_RAW, fgk.H_SYM | fgk.H_DROP_ZEROS):
+        A = H.projected_csr(dets, mode, packed=True, index=idx, sort_rows=True)
+        assert A.nnz > 5 * n                                 # rows do have in-basis connections
+        for flag in (fgk.H_HASH_WALK, fgk.H_FLAT_WALK):
+            B = H.projected_csr(dets, mode | flag, packed=True, index=idx, sort_rows=True)
+            assert torch.equal(A.row_ptr, B.row_ptr) and torch.equal(A.cols, B.cols) and torch.equal(A.vals, B.vals)
+            del B
+    A = H.projected_csr(dets, fgk.H_SYM, packed=True, index=idx)
+    x = torch.from_numpy(rng.standard_normal(n)).cuda()
+    y = A.matvec(x)
+    Ab = H.projected_csr(dets, fgk.H_SYM, packed=True, index=idx, row_begin=1234, row_end=n - 77)
+    assert float((Ab.matvec(x) - y[1234:n - 77]).abs().max()) < 1e-10
+    Q = H.projected_sell(dets, fgk.H_SYM, packed=True, index=idx)
+    assert Q.nnz == A.nnz and float((Q.matvec(x) - y).abs().max()) < 1e-10
 
 
 def test_config5_shape_pt2_96_sites(fgk):
@@ -733,7 +782,7 @@ def test_random_shapes_on_device(fgk, seed):
     D = O.dense_H(dets)
     off = ~np.eye(n, dtype=bool)
     for mode, ref in ((fgk.H_RAW, D), (fgk.H_SYM, 0.5 * (D + D.T))):
-        for flag in (0, fgk.H_FLAT_WALK):
+        for flag in (0, fgk.H_FLAT_WALK, fgk.H_HASH_WALK):
             A = H.projected_csr(t64(dets), mode | flag).to_scipy().toarray()
             assert np.array_equal(A[off], ref[off])
             assert np.abs(np.diag(A) - np.diag(ref)).max() < TOL
