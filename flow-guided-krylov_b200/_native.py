@@ -54,7 +54,7 @@ _SIGNATURES = {
     "fgk_peer_free": (ci, [vp, ci]),
     "fgk_spmv_sell_f64_allgather": (ci, [i64, vp, vp, vp, vp, C.POINTER(vp), ci, i64, ci, vp]),
     "fgk_peer_barrier": (ci, [C.POINTER(vp), ci, ci, C.c_uint64, vp, ci, vp]),
-    "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, vp, ci, C.POINTER(vp)]),
+    "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, ci, C.POINTER(vp)]),
     "fgk_pt2_destroy": (ci, [vp]),
     "fgk_pt2_set_partition": (ci, [vp, ci, ci, i64, vp, vp, vp]),
     "fgk_pt2_reset": (ci, [vp, vp]),

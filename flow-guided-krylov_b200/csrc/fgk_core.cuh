@@ -110,10 +110,10 @@ FGK_HD int sign2_parity(u64 a, u64 b, int n_orb, int p, int r, int q, int s)
     return t & 1;
 }
 
-// index into an (n,n,n,n) table
+// index into an (n,n,n,n) table; n <= 64, so the index (< 2^24) fits 32-bit arithmetic
 FGK_HD size_t idx4(int n, int x, int y, int z, int u)
 {
-    return (((size_t)x * n + y) * n + z) * n + u;
+    return (size_t)(unsigned)(((x * n + y) * n + z) * n + u);
 }
 
 // decode t in [0, m(m-1)/2) -> (k<l), row-major over k (the i<j / k<l loops of

@@ -72,8 +72,7 @@ struct fgk_index {
 struct Pt2View {
     u64* table;         // (tag << 32 | slot), empty = ~0
     u64 mask;           // table_slots - 1
-    fgk_det* keys;      // pool
-    double* sums;
+    u64* pool;          // 4 words per slot: {alpha, beta, FP64 accumulator bits, spare}
     i64 capacity;
     unsigned long long* counters;   // [0] slots used, [1] raw candidates tested, [2] overflow
     // The table is split into 2^region_bits regions selected by the TOP hash bits; linear

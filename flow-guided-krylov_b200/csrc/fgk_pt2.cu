@@ -4,7 +4,7 @@
 // reference's get_connections(j) emits): every connection x that is not in the
 // basis adds c_j * <x|H|j> to the FP64 accumulator of x in a device hash map
 // (open addressing; 64-bit table entries tag<<32|slot pointing into a pool of
-// 16-byte keys + 8-byte sums).  This is phase 1 of
+// 32-byte entries {key, FP64 sum}).  This is phase 1 of
 // SelectedCIExpander._find_important_configs (residual_expansion.py:498-522) --
 // there a Python dict keyed by hash(bytes).  fgk_pt2_export is phase 2
 // (:527-548): diagonal of every candidate and coupling^2 / (|E - E_x| + 1e-10).
@@ -19,7 +19,12 @@ __device__ __forceinline__ void atomic_max_abs(double* addr, double v)
               (unsigned long long)__double_as_longlong(fabs(v)));
 }
 
-// insert-or-accumulate; returns false on pool overflow
+// insert-or-accumulate; returns false on pool overflow.
+// Pool entry = 32 bytes {alpha, beta, FP64 accumulator, spare}: the key compare and the
+// accumulation of a repeat candidate touch ONE 32-byte sector (two with separate key / sum
+// arrays -- the sweep is bound by random DRAM sectors).  A new entry is written complete,
+// first contribution included, before the table slot is published, so the pool needs no
+// clearing between sweeps and a new candidate costs no accumulator atomic.
 __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, double val, int mode)
 {
     const u64 tag = h >> 32;
@@ -36,26 +41,25 @@ __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, d
             if (mine < 0) {
                 mine = (long long)atomicAdd(W.counters, 1ull);
                 if (mine >= W.capacity) { atomicExch(W.counters + 2, 1ull); ok = false; break; }
-                reinterpret_cast<ulonglong2*>(W.keys)[mine] = make_ulonglong2(o.a, o.b);
+                ulonglong2* p = reinterpret_cast<ulonglong2*>(W.pool + 4 * mine);
+                const double v0 = mode == FGK_PT2_MAXABS ? fabs(val) : val;
+                p[0] = make_ulonglong2(o.a, o.b);
+                p[1] = make_ulonglong2((u64)__double_as_longlong(v0), 0ull);
                 __threadfence();
             }
             u64 prev = atomicCAS((unsigned long long*)(W.table + slot), FGK_EMPTY,
                                  (tag << 32) | (u64)(unsigned)mine);
-            if (prev == FGK_EMPTY) {
-                if (mode == FGK_PT2_MAXABS) atomic_max_abs(W.sums + mine, val);
-                else atomicAdd(W.sums + mine, val);
-                mine = -1;
-                break;
-            }
+            if (prev == FGK_EMPTY) { mine = -1; break; }      // published, contribution inside
             e = prev;               // somebody else took the slot: inspect it
         }
         if ((e >> 32) == tag) {
             unsigned ps = (unsigned)(e & 0xffffffffu);
-            // L2 read: the key was published with __threadfence before the CAS
-            ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(W.keys) + ps);
+            // L2 read: the entry was published with __threadfence before the CAS
+            u64* p = W.pool + 4 * (u64)ps;
+            ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(p));
             if (k.x == o.a && k.y == o.b) {
-                if (mode == FGK_PT2_MAXABS) atomic_max_abs(W.sums + ps, val);
-                else atomicAdd(W.sums + ps, val);
+                if (mode == FGK_PT2_MAXABS) atomic_max_abs(reinterpret_cast<double*>(p + 2), val);
+                else atomicAdd(reinterpret_cast<double*>(p + 2), val);
                 break;
             }
         }
@@ -63,7 +67,7 @@ __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, d
         slot = base + local;
     }
     if (mine >= 0 && mine < W.capacity)   // allocated but lost the race: mark the slot dead
-        reinterpret_cast<ulonglong2*>(W.keys)[mine] = make_ulonglong2(FGK_EMPTY, FGK_EMPTY);
+        *reinterpret_cast<ulonglong2*>(W.pool + 4 * mine) = make_ulonglong2(FGK_EMPTY, FGK_EMPTY);
     return ok;
 }
 
@@ -229,8 +233,11 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
         const i64 k = it * stride + (i64)blockIdx.x * blockDim.x + threadIdx.x;
         bool live = false;
         ulonglong2 d = make_ulonglong2(0, 0);
+        ulonglong2 acc = make_ulonglong2(0, 0);
         if (k < n_slots) {
-            d = reinterpret_cast<const ulonglong2*>(W.keys)[k];
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(W.pool + 4 * k);
+            d = p[0];
+            acc = p[1];
             live = !(d.x == FGK_EMPTY && d.y == FGK_EMPTY);
         }
         unsigned b = __ballot_sync(0xffffffffu, live);
@@ -240,7 +247,7 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
         base = __shfl_sync(0xffffffffu, base, 0);
         if (!live) continue;
         const i64 o = (i64)base + __popc(b & ((1u << lane) - 1u));
-        const double cpl = W.sums[k];
+        const double cpl = __longlong_as_double((long long)acc.x);
         if (out_dets) reinterpret_cast<ulonglong2*>(out_dets)[o] = d;
         if (out_coupling) out_coupling[o] = cpl;
         if (have_h) {
@@ -253,22 +260,21 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
     }
 }
 
-extern "C" int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* keys,
-                              double* sums, uint64_t* counters, int device, fgk_pt2_t* out)
+extern "C" int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* pool,
+                              uint64_t* counters, int device, fgk_pt2_t* out)
 {
-    if (!out || capacity < 1 || !table || !keys || !sums || !counters)
+    if (!out || capacity < 1 || !table || !pool || !counters)
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: bad argument");
     if (capacity >= (1ll << 32) - 1) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_pt2_create: capacity >= 2^32");
     if (table_slots < 2 || (table_slots & (table_slots - 1)) || table_slots < capacity)
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: table_slots must be a power of two >= capacity");
-    if ((uintptr_t)keys & 15) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: keys must be 16-byte aligned");
+    if ((uintptr_t)pool & 31) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: pool must be 32-byte aligned");
     fgk_pt2* P = new fgk_pt2();
     P->device = device;
     P->v.capacity = capacity;
     P->v.mask = (u64)table_slots - 1;
     P->v.table = (u64*)table;
-    P->v.keys = (fgk_det*)keys;
-    P->v.sums = sums;
+    P->v.pool = (u64*)pool;
     P->v.counters = (unsigned long long*)counters;
     P->v.region_bits = 0;
     P->v.region_mask = P->v.mask;
@@ -316,7 +322,6 @@ extern "C" int fgk_pt2_reset(fgk_pt2_t ws, void* stream)
     FGK_CUDA(cudaSetDevice(ws->device));
     cudaStream_t st = (cudaStream_t)stream;
     FGK_CUDA(cudaMemsetAsync(ws->v.table, 0xFF, (ws->v.mask + 1) * sizeof(u64), st));
-    FGK_CUDA(cudaMemsetAsync(ws->v.sums, 0, (size_t)ws->v.capacity * sizeof(double), st));
     FGK_CUDA(cudaMemsetAsync(ws->v.counters, 0, 4 * sizeof(unsigned long long), st));
     if (ws->v.queue_bits)
         FGK_CUDA(cudaMemsetAsync(ws->v.qcursors, 0, sizeof(unsigned long long) << ws->v.queue_bits, st));

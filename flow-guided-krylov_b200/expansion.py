@@ -48,18 +48,17 @@ class Pt2Workspace:
         while slots < 2 * self.capacity:
             slots *= 2
         slots = max(slots, 1024)
-        # caller-allocated (torch caching allocator): table, key pool, accumulators, counters
+        # caller-allocated (torch caching allocator): table, pool of 32-byte {key, sum} entries, counters
         self._table = torch.empty(slots, dtype=torch.int64, device=device)
-        self._keys = torch.empty(self.capacity, 2, dtype=torch.int64, device=device)
-        self._sums = torch.empty(self.capacity, dtype=torch.float64, device=device)
+        self._pool = torch.empty(self.capacity, 4, dtype=torch.int64, device=device)
         self._counters = torch.zeros(4, dtype=torch.int64, device=device)
         h = C.c_void_p()
         nat.check(nat.lib().fgk_pt2_create(
-            self.capacity, slots, nat.ptr(self._table), nat.ptr(self._keys), nat.ptr(self._sums),
+            self.capacity, slots, nat.ptr(self._table), nat.ptr(self._pool),
             nat.ptr(self._counters), nat.device_index(device), C.byref(h)))
         self._h = h
         self.queue_pairs = 0
-        foot = 8 * slots + 24 * self.capacity
+        foot = 8 * slots + 32 * self.capacity
         if queue_pairs == "auto":
             queue_pairs = 2 * self.capacity if foot > 4 * self.L2_REGION_BYTES else None
         if queue_pairs:
@@ -216,10 +215,10 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
 def default_pt2_capacity(ham, n_sources, partition=False):
     """distinct-candidate capacity for a sweep over n_sources determinants: every raw
     connection could be a distinct candidate; bounded by the free HBM.  Per unit of capacity:
-    16 B table + 24 B pool + 24 B export buffers, plus 2 x 30 B of partition queue."""
+    16 B table + 32 B pool + 24 B export buffers, plus 2 x 30 B of partition queue."""
     n_conn = _raw_connections_per_det(ham)
     free = nat.device_info(ham.device)["free_bytes"]
-    per = 64 + (60 if partition else 0) + 8
+    per = 72 + (60 if partition else 0) + 8
     return int(min(max(4096, 1.05 * n_sources * n_conn), 0.8 * free / per, 2 ** 31))
 
 

@@ -51,8 +51,10 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
     m_max = min(n, max_space if max_space is not None else max(12 * k, 36))
     m_max = max(m_max, nb + k)
     keep = min(max(2 * k + 2, m_max // 3), m_max - k)
-    V = torch.zeros(n, m_max, dtype=torch.float64, device=dev)
-    W = torch.zeros(n, m_max, dtype=torch.float64, device=dev)
+    # basis vectors are the ROWS of V / W (each one contiguous): the n x m products below are
+    # then plain column-major GEMVs/GEMMs with leading dimension n, and H.v reads V[j] in place
+    V = torch.zeros(m_max, n, dtype=torch.float64, device=dev)
+    W = torch.zeros(m_max, n, dtype=torch.float64, device=dev)
     start = torch.argsort(diag)[:nb]
     V0 = torch.zeros(n, nb, dtype=torch.float64, device=dev)
     V0[start, torch.arange(nb, device=dev)] = 1.0
@@ -64,20 +66,21 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         V0[:, 0] = v0.to(dev, torch.float64)
     V0, _ = torch.linalg.qr(V0)
     m = nb
-    V[:, :m] = V0
+    V[:m] = V0.T
+    del V0
     for i in range(m):
-        W[:, i] = mv(V[:, i].contiguous())
+        W[i] = mv(V[i])
     T = np.zeros((m_max, m_max))
-    T[:m, :m] = (V[:, :m].T @ W[:, :m]).cpu().numpy()
+    T[:m, :m] = (V[:m] @ W[:m].T).cpu().numpy()
     w_out = X = None
     for _ in range(max_iter):
         Tm = 0.5 * (T[:m, :m] + T[:m, :m].T)
         th, s = np.linalg.eigh(Tm)
-        s_dev = torch.from_numpy(np.ascontiguousarray(s)).to(dev)
+        s_dev = torch.from_numpy(np.ascontiguousarray(s.T)).to(dev)     # rows = Ritz vectors
         thk = torch.from_numpy(th[:k].copy()).to(dev)
-        X = V[:, :m] @ s_dev[:, :k]
-        R = W[:, :m] @ s_dev[:, :k] - X * thk
-        rn = torch.linalg.norm(R, dim=0).cpu().numpy()
+        X = s_dev[:k] @ V[:m]                                           # (k, n)
+        R = s_dev[:k] @ W[:m] - thk[:, None] * X
+        rn = torch.linalg.norm(R, dim=1).cpu().numpy()
         w_out = thk
         scale = max(1.0, float(np.abs(th[:k]).max()))
         if rn.max() < tol * scale:
@@ -85,8 +88,8 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         todo = [i for i in range(k) if rn[i] >= tol * scale]
         if m + len(todo) > m_max:                   # thick restart: rotate V and H V together
             q = keep
-            V[:, :q] = V[:, :m] @ s_dev[:, :q]
-            W[:, :q] = W[:, :m] @ s_dev[:, :q]
+            V[:q] = s_dev[:q] @ V[:m]
+            W[:q] = s_dev[:q] @ W[:m]
             T[:] = 0.0
             T[np.arange(q), np.arange(q)] = th[:q]
             m = q
@@ -94,22 +97,22 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         for i in todo:
             den = thk[i] - diag
             den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
-            t = R[:, i] / den
+            t = R[i] / den
             for _ in range(2):                      # CGS2 against everything kept so far
-                t = t - V[:, :m + added] @ (V[:, :m + added].T @ t)
+                t = t - (V[:m + added] @ t) @ V[:m + added]
             nt = float(torch.linalg.norm(t))
             if nt > 1e-10:
-                V[:, m + added] = t / nt
+                V[m + added] = t / nt
                 added += 1
         if added == 0:
             break
         for j in range(m, m + added):
-            W[:, j] = mv(V[:, j].contiguous())
-        blk = (V[:, :m + added].T @ W[:, m:m + added]).cpu().numpy()     # new columns of T
+            W[j] = mv(V[j])
+        blk = (V[:m + added] @ W[m:m + added].T).cpu().numpy()     # new columns of T
         T[:m + added, m:m + added] = blk
         T[m:m + added, :m + added] = blk.T
         m += added
-    return w_out.clone(), X.clone()
+    return w_out.clone(), X.T.contiguous()
 
 
 # Al-Mohy & Higham 2011, table 3.1 (tol = 2^-53): theta_m for selected m

@@ -207,12 +207,13 @@ int fgk_peer_barrier(uint64_t* const* peer_flags, int rank, int world, uint64_t 
  * The workspace is a device hash map determinant -> FP64 accumulator with room for
  * `capacity` distinct candidates.  All of its memory is the caller's:
  *   table    uint64[table_slots]   (table_slots a power of two, >= 2*capacity advised)
- *   keys     uint64[capacity][2]   (16-byte aligned)
- *   sums     double[capacity]
+ *   pool     uint64[capacity][4]   (32-byte aligned; one entry = {alpha, beta, FP64
+ *                                   accumulator, spare}: key and sum share a 32-byte sector)
  *   counters uint64[4]
- * fgk_pt2_create only wraps them in a handle; call fgk_pt2_reset before use. */
-int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* keys,
-                   double* sums, uint64_t* counters, int device, fgk_pt2_t* out);
+ * fgk_pt2_create only wraps them in a handle; call fgk_pt2_reset before use (it clears the
+ * table and the counters; pool entries are written complete when they are claimed). */
+int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* pool,
+                   uint64_t* counters, int device, fgk_pt2_t* out);
 int fgk_pt2_destroy(fgk_pt2_t ws);
 /* Optional radix partition in front of the hash (large sweeps, whose accumulator is far
  * bigger than L2): the table is split into 2^region_bits regions chosen by the top hash bits
