@@ -223,7 +223,7 @@ k_diag(HamView H, unsigned tab_bytes, const fgk_det* __restrict__ dets, i64 n, d
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
         ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + j);
         fgk_det dd = {d.x, d.y};
-        out[j] = tab_bytes ? diag_element(H, dd, [](const double* p) { return *p; })
+        out[j] = tab_bytes ? diag_element(H, dd, LdsD())
                            : diag_element(H, dd, [](const double* p) { return __ldg(p); });
     }
 }

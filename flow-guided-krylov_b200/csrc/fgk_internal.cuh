@@ -139,6 +139,17 @@ __device__ __forceinline__ void tma_stage_table(void* smem_dst, const void* gmem
 struct LdgF { __device__ __forceinline__ float operator()(const float* p) const { return __ldg(p); } };
 struct LdgD { __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); } };
 
+// explicit shared-space load for tables staged in shared memory (a table pointer rebased onto
+// the staging buffer is a generic address to the compiler: it emits LD instead of LDS)
+struct LdsD {
+    __device__ __forceinline__ double operator()(const double* p) const
+    {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        return v;
+    }
+};
+
 struct WarpLists { uint8_t occ_a[64], virt_a[64], occ_b[64], virt_b[64]; };
 
 // one lane per orbital builds the ascending occupied / virtual lists of d

@@ -78,23 +78,27 @@ template <class FS, class FD>
 __device__ __forceinline__ void warp_enumerate_split(const DetCtx& c, int lane, int split, int n_split,
                                                      FS&& fs, FD&& fd)
 {
-    int chunk = 0;
-    for (int t0 = 0; t0 < c.n_s; t0 += 32, chunk++) {
-        if (chunk % n_split != split) continue;
-        int t = t0 + lane, p = 0, q = 0;
-        bool va = false, vb = false;
-        if (t < c.n_s) decode_single(c, t, p, q, va, vb);
-        fs(va, vb, p, q);
-    }
-#pragma unroll 1
-    for (int st = 2; st <= 4; st++) {
-        const int size = st == 2 ? c.n_aa : (st == 3 ? c.n_bb : c.n_ab);
-        for (int t0 = 0; t0 < size; t0 += 32, chunk++) {
-            if (chunk % n_split != split) continue;
-            int t = t0 + lane;
+    // chunk g of the concatenated index spaces [singles | aa | bb | ab], each padded to 32;
+    // this warp takes g = split, split + n_split, ... (a strided loop: walking every chunk and
+    // skipping the foreign ones cost 45 % of the kernel's instructions, ncu r01l)
+    const int c0 = (c.n_s + 31) >> 5;
+    const int c1 = c0 + ((c.n_aa + 31) >> 5);
+    const int c2 = c1 + ((c.n_bb + 31) >> 5);
+    const int c3 = c2 + ((c.n_ab + 31) >> 5);
+    for (int g = split; g < c3; g += n_split) {
+        if (g < c0) {
+            int t = g * 32 + lane, p = 0, q = 0;
+            bool va = false, vb = false;
+            if (t < c.n_s) decode_single(c, t, p, q, va, vb);
+            fs(va, vb, p, q);
+        } else {
+            const int st = g < c1 ? 2 : (g < c2 ? 3 : 4);
+            const int base = st == 2 ? c0 : (st == 3 ? c1 : c2);
+            const int size = st == 2 ? c.n_aa : (st == 3 ? c.n_bb : c.n_ab);
+            const int t = (g - base) * 32 + lane;
             Excitation x;
             x.cls = st; x.h0 = x.h1 = x.e0 = x.e1 = 0;
-            bool valid = t < size;
+            const bool valid = t < size;
             if (valid) decode_double(c, st, t, x);
             fd(valid, x);
         }
@@ -252,7 +256,7 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
         if (out_coupling) out_coupling[o] = cpl;
         if (have_h) {
             fgk_det dd = {d.x, d.y};
-            double ex = staged ? diag_element(H, dd, [](const double* p) { return *p; })
+            double ex = staged ? diag_element(H, dd, LdsD())
                                : diag_element(H, dd, [](const double* p) { return __ldg(p); });
             if (out_diag) out_diag[o] = ex;
             if (out_importance) out_importance[o] = cpl * cpl / (fabs(energy - ex) + 1e-10);   // :547-548

@@ -166,11 +166,16 @@ def select_top_k(dets, score, k, n_orb, tie_eps=1e-9):
 
 
 def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
-                   coeff_cut=1e-8, max_passes=64, src_shard=None):
+                   coeff_cut=1e-8, max_passes=4096, src_shard=None):
     """Phase 1+2 of _find_important_configs (residual_expansion.py:481-548) for the
     sources of `index` (src_shard=(rank, world): only every world-th significant source,
     the multi-GPU split -- the significant sources, not the rows, are what must balance).
-    Returns (cand_dets, coupling, diag, importance, stats)."""
+    Returns (cand_dets, coupling, diag, importance, stats).
+
+    Pool slots are claimed before the table slot is won, so threads that meet the same new
+    candidate at the same time each use one (the losers' slots are marked dead): a pass needs
+    room for up to its RAW candidates in the worst case, which is what default_pt2_capacity
+    provides; an undersized workspace just takes more passes."""
     dev = ham.device
     n = len(index)
     c32 = coeffs.to(dev).to(torch.float32)                         # :481

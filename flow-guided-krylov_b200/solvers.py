@@ -24,8 +24,26 @@ def _full_matvec(P, x):
     return P.matvec(x)
 
 
+class _Phases:
+    """optional wall-clock split of the Davidson loop (synchronises; diagnostics only)."""
+
+    def __init__(self, sink, dev):
+        self.sink, self.dev, self.t = sink, dev, None
+
+    def mark(self, name):
+        if self.sink is None:
+            return
+        import time
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        now = time.perf_counter()
+        if self.t is not None and name:
+            self.sink[name] = self.sink.get(name, 0.0) + now - self.t
+        self.t = now
+
+
 def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=None,
-                      diagonal=None, dense_max=DENSE_EIG_MAX, v0=None):
+                      diagonal=None, dense_max=DENSE_EIG_MAX, v0=None, phases=None):
     """k lowest eigenpairs of the symmetric operator P (a ProjectedH built with
     H_SYM, or any object with .n plus `matvec`/`diagonal` callables).
     Returns (w (k,) float64 tensor ascending, V (n,k)).
@@ -45,6 +63,8 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         return w[:k].clone(), v[:, :k].clone()
     diag = diagonal if diagonal is not None else P.diagonal()
     dev = diag.device
+    ph = _Phases(phases, dev)
+    ph.mark(None)
     if matvec is None and hasattr(P, "optimize_for_matvec"):
         P.optimize_for_matvec()                    # many products ahead: SELL-32 / packed storage
     nb = min(max(2 * k, k + 2), n)                 # initial block: lowest diagonal entries
@@ -60,8 +80,8 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
     V0[start, torch.arange(nb, device=dev)] = 1.0
     # A seeded random admixture: unit vectors alone can be orthogonal to a whole
     # symmetry sector (e.g. triplets), which residual norms cannot detect.
-    gen = torch.Generator(device="cpu").manual_seed(20240229)
-    V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(20240229)
+    V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen, device=dev)
     if v0 is not None:
         V0[:, 0] = v0.to(dev, torch.float64)
     V0, _ = torch.linalg.qr(V0)
@@ -73,6 +93,7 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
     T = np.zeros((m_max, m_max))
     T[:m, :m] = (V[:m] @ W[:m].T).cpu().numpy()
     w_out = X = None
+    ph.mark("setup")
     for _ in range(max_iter):
         Tm = 0.5 * (T[:m, :m] + T[:m, :m].T)
         th, s = np.linalg.eigh(Tm)
@@ -81,6 +102,7 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         X = s_dev[:k] @ V[:m]                                           # (k, n)
         R = s_dev[:k] @ W[:m] - thk[:, None] * X
         rn = torch.linalg.norm(R, dim=1).cpu().numpy()
+        ph.mark("ritz_residual")
         w_out = thk
         scale = max(1.0, float(np.abs(th[:k]).max()))
         if rn.max() < tol * scale:
@@ -104,14 +126,17 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
             if nt > 1e-10:
                 V[m + added] = t / nt
                 added += 1
+        ph.mark("correction_orth")
         if added == 0:
             break
         for j in range(m, m + added):
             W[j] = mv(V[j])
+        ph.mark("matvec")
         blk = (V[:m + added] @ W[m:m + added].T).cpu().numpy()     # new columns of T
         T[:m + added, m:m + added] = blk
         T[m:m + added, :m + added] = blk.T
         m += added
+        ph.mark("project")
     return w_out.clone(), X.T.contiguous()
 
 
