@@ -274,6 +274,9 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout carries the one
+        # JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     def barrier():
