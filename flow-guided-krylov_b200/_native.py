@@ -58,6 +58,8 @@ _SIGNATURES = {
     "fgk_pt2_destroy": (ci, [vp]),
     "fgk_pt2_set_partition": (ci, [vp, ci, ci, i64, vp, vp, vp]),
     "fgk_pt2_reset": (ci, [vp, vp]),
+    "fgk_pt2_score": (ci, [vp, vp, i64, dbl, i64, vp, vp, C.POINTER(i64), C.POINTER(i64), vp]),
+    "fgk_pt2_gather": (ci, [vp, i64, vp, vp, vp, i64, C.POINTER(i64), vp]),
     "fgk_pt2_accumulate": (ci, [vp, vp, vp, vp, vp, i64, ci, ci, ci, vp]),
     "fgk_pt2_merge": (ci, [vp, vp, vp, i64, ci, vp]),
     "fgk_pt2_count": (ci, [vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(ci)]),

@@ -264,6 +264,168 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
     }
 }
 
+// ---- streaming selection: score in place -> exponent histogram -> gather the head ----------
+// The top-k of a sweep never needs the full candidate list on the host side of the ABI:
+// k_pt2_score writes every live candidate's score (importance, or max |c.H| in MAXABS mode)
+// into the spare word of its pool entry and counts scores per binary exponent (2,048 bins,
+// shared-memory histogram per CTA); k_pt2_threshold walks the bins from the top until k
+// candidates are covered and steps one more bin down (covers the caller's relative tie band);
+// k_pt2_gather compacts the candidates at or above that bound.  The caller then orders a few
+// thousand candidates instead of running a top-k over tens of millions.
+static const int PT2_BINS = 2048;      // sign + 11 exponent bits of a non-negative double
+
+__global__ void __launch_bounds__(1024)
+k_pt2_score(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, double energy,
+            unsigned* __restrict__ hist)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ unsigned s_hist[PT2_BINS];
+    const bool staged = have_h && tab_bytes;
+    for (int b = threadIdx.x; b < PT2_BINS; b += blockDim.x) s_hist[b] = 0;
+    if (staged) {
+        tma_stage_table(s_raw, H.hdiag, tab_bytes, &s_mbar);
+        const double* s_tab = reinterpret_cast<const double*>(s_raw);
+        const double* g0 = H.hdiag;
+        H.nib_jk = s_tab + (H.nib_jk - g0);
+        H.nib_jab = s_tab + (H.nib_jab - g0);
+        H.hdiag = s_tab;
+    }
+    __syncthreads();
+    i64 live_count = 0;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_slots; k += (i64)gridDim.x * blockDim.x) {
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(W.pool + 4 * k);
+        const ulonglong2 d = p[0];
+        if (d.x == FGK_EMPTY && d.y == FGK_EMPTY) continue;
+        ulonglong2 acc = p[1];
+        const double cpl = __longlong_as_double((long long)acc.x);
+        double score = fabs(cpl);
+        if (have_h) {
+            fgk_det dd = {d.x, d.y};
+            const double ex = staged ? diag_element(H, dd, LdsD())
+                                     : diag_element(H, dd, [](const double* q) { return __ldg(q); });
+            score = cpl * cpl / (fabs(energy - ex) + 1e-10);      // residual_expansion.py:547-548
+        }
+        acc.y = (u64)__double_as_longlong(score);
+        p[1] = acc;
+        atomicAdd(&s_hist[(unsigned)(acc.y >> 52) & (PT2_BINS - 1)], 1u);
+        live_count++;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < PT2_BINS; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(hist + b, s_hist[b]);
+    live_count = warp_sum_i64(live_count);
+    if ((threadIdx.x & 31) == 0 && live_count) atomicAdd(W.counters + 3, (unsigned long long)live_count);
+}
+
+// thr[0] = lowest score bit pattern to keep, thr[1] = how many candidates that keeps
+__global__ void k_pt2_threshold(const unsigned* __restrict__ hist, i64 k, unsigned long long* thr)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long cum = 0;
+    int b = PT2_BINS - 1;
+    for (; b >= 0; b--) {
+        cum += hist[b];
+        if ((i64)cum >= k) break;
+    }
+    if (b > 0) { b--; cum += hist[b]; }          // one bin of slack below the k-th score
+    if (b < 0) b = 0;
+    thr[0] = (unsigned long long)b << 52;
+    thr[1] = cum;
+}
+
+__global__ void __launch_bounds__(256)
+k_pt2_gather(Pt2View W, i64 n_slots, const unsigned long long* __restrict__ thr, fgk_det* __restrict__ out_dets,
+             double* __restrict__ out_score, i64 cap, unsigned long long* cursor)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long lo = thr[0];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 rounds = (n_slots + stride - 1) / stride;
+    for (i64 it = 0; it < rounds; it++) {
+        const i64 k = it * stride + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool take = false;
+        ulonglong2 d = make_ulonglong2(0, 0), acc = make_ulonglong2(0, 0);
+        if (k < n_slots) {
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(W.pool + 4 * k);
+            d = p[0];
+            acc = p[1];
+            take = !(d.x == FGK_EMPTY && d.y == FGK_EMPTY) && acc.y >= lo && !(acc.y >> 63);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, take);
+        if (!b) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!take) continue;
+        const i64 o = (i64)base + __popc(b & ((1u << lane) - 1u));
+        if (o < cap) {
+            reinterpret_cast<ulonglong2*>(out_dets)[o] = d;
+            out_score[o] = __longlong_as_double((long long)acc.y);
+        }
+    }
+}
+
+extern "C" int fgk_pt2_score(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy, int64_t k,
+                             uint32_t* hist, uint64_t* thr, int64_t* n_live, int64_t* n_keep, void* stream)
+{
+    if (!ws || !hist || !thr || k < 0) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_score: bad argument");
+    if (n_slots < 0 || n_slots > ws->v.capacity) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_score: bad n_slots");
+    if (n_live) *n_live = 0;
+    if (n_keep) *n_keep = 0;
+    if (n_slots == 0) return FGK_OK;
+    FGK_CUDA(cudaSetDevice(ws->device));
+    HamView hv;
+    if (h) hv = h->v; else { hv = HamView(); }
+    const unsigned tab_bytes = h ? h->dtab_bytes : 0;
+    static bool attr_set[64] = {false};
+    if (tab_bytes > 32 * 1024 && !attr_set[ws->device & 63]) {
+        FGK_CUDA(cudaFuncSetAttribute(k_pt2_score, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        attr_set[ws->device & 63] = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    FGK_CUDA(cudaMemsetAsync(ws->v.counters + 3, 0, sizeof(unsigned long long), st));
+    FGK_CUDA(cudaMemsetAsync(hist, 0, PT2_BINS * sizeof(unsigned), st));
+    i64 need = (n_slots + 1023) / 1024, cap = (i64)fgk_sm_count(ws->device) * 2;
+    k_pt2_score<<<(int)(need < cap ? need : cap), 1024, tab_bytes, st>>>(
+        hv, h != nullptr, tab_bytes, ws->v, n_slots, energy, (unsigned*)hist);
+    FGK_LAUNCH_CHECK();
+    k_pt2_threshold<<<1, 32, 0, st>>>((const unsigned*)hist, k, (unsigned long long*)thr);
+    FGK_LAUNCH_CHECK();
+    unsigned long long host[3] = {0, 0, 0};
+    FGK_CUDA(cudaMemcpyAsync(host, thr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FGK_CUDA(cudaMemcpyAsync(host + 2, ws->v.counters + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FGK_CUDA(cudaStreamSynchronize(st));
+    if (n_keep) *n_keep = (int64_t)host[1];
+    if (n_live) *n_live = (int64_t)host[2];
+    return FGK_OK;
+}
+
+extern "C" int fgk_pt2_gather(fgk_pt2_t ws, int64_t n_slots, const uint64_t* thr, uint64_t* out_dets,
+                              double* out_score, int64_t out_cap, int64_t* n_written, void* stream)
+{
+    if (!ws || !thr) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_gather: bad argument");
+    if (n_written) *n_written = 0;
+    if (n_slots == 0 || out_cap == 0) return FGK_OK;
+    if (n_slots < 0 || n_slots > ws->v.capacity || out_cap < 0 || !out_dets || !out_score)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_gather: bad argument");
+    FGK_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FGK_CUDA(cudaMemsetAsync(ws->v.counters + 3, 0, sizeof(unsigned long long), st));
+    i64 need = (n_slots + 255) / 256, cap = (i64)fgk_sm_count(ws->device) * 8;
+    k_pt2_gather<<<(int)(need < cap ? need : cap), 256, 0, st>>>(
+        ws->v, n_slots, (const unsigned long long*)thr, (fgk_det*)out_dets, out_score, out_cap,
+        ws->v.counters + 3);
+    FGK_LAUNCH_CHECK();
+    unsigned long long w = 0;
+    FGK_CUDA(cudaMemcpyAsync(&w, ws->v.counters + 3, sizeof(w), cudaMemcpyDeviceToHost, st));
+    FGK_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)w > out_cap) return fgk_fail(FGK_ERR_CAPACITY, "fgk_pt2_gather: %lld candidates, room for %lld",
+                                              (long long)w, (long long)out_cap);
+    if (n_written) *n_written = (int64_t)w;
+    return FGK_OK;
+}
+
 extern "C" int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* pool,
                               uint64_t* counters, int device, fgk_pt2_t* out)
 {

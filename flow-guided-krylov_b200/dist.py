@@ -218,13 +218,12 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
                 ok = False
                 break
             raw += nr
-            want_c = mode != nat.PT2_SUM
-            d, cpl, _, imp = wa.export(ham, ns, energy, want_coupling=want_c, want_diag=False)
-            uniq += int(d.shape[0])
-            sd, ss = select_top_k(d, imp if mode == nat.PT2_SUM else cpl, k, ham.n_orbitals)
+            d, sc, live = wa.select_head(ham if mode == nat.PT2_SUM else None, ns, energy, k)
+            uniq += live
+            sd, ss = select_top_k(d, sc, k, ham.n_orbitals)
             keep_d.append(sd.clone())
             keep_s.append(ss.clone())
-            del d, cpl, imp
+            del d, sc
         if ok:
             break
         local_passes *= 2

@@ -130,6 +130,34 @@ class Pt2Workspace:
                 dg[:m] if dg is not None else None, imp[:m])
 
 
+def _ws_select_head(self, ham, n_slots, energy, k):
+    """Candidates that can be among the k best of this sweep, scored in place
+    (fgk_pt2_score + fgk_pt2_gather): -> (dets, scores, n_live).  ham=None scores by
+    |coupling| (MAXABS sweeps), else by the PT2 importance.  The head holds every candidate
+    down to one binary exponent below the k-th score, so select_top_k on it equals
+    select_top_k on the full list."""
+    dev = self.device
+    if getattr(self, "_hist", None) is None:
+        self._hist = torch.empty(2048, dtype=torch.int32, device=dev)
+        self._thr = torch.empty(2, dtype=torch.int64, device=dev)
+    live, keep = C.c_int64(0), C.c_int64(0)
+    nat.check(nat.lib().fgk_pt2_score(
+        ham._h if ham is not None else None, self._h, n_slots, float(energy), int(k),
+        nat.ptr(self._hist), nat.ptr(self._thr), C.byref(live), C.byref(keep), nat.stream_ptr(dev)))
+    m = keep.value
+    dets = torch.empty(m, 2, dtype=torch.int64, device=dev)
+    score = torch.empty(m, dtype=torch.float64, device=dev)
+    wrote = C.c_int64(0)
+    if m:
+        nat.check(nat.lib().fgk_pt2_gather(self._h, n_slots, nat.ptr(self._thr), nat.ptr(dets, torch.int64),
+                                           nat.ptr(score, torch.float64), m, C.byref(wrote),
+                                           nat.stream_ptr(dev)))
+    return dets[:wrote.value], score[:wrote.value], live.value
+
+
+Pt2Workspace.select_head = _ws_select_head
+
+
 def _key_sort_order(dets, n_orb):
     """argsort of packed determinants by ascending unsigned (alpha, beta)."""
     a, b = dets[:, 0], dets[:, 1]
@@ -270,13 +298,12 @@ def pt2_select(ham, index, coeffs, energy, k, workspace=None, mode=nat.PT2_SUM, 
                 ok = False
                 break
             raw += nr
-            want_c = mode != nat.PT2_SUM
-            d, cpl, _, imp = ws.export(ham, ns, energy, want_coupling=want_c, want_diag=False)
-            uniq += int(d.shape[0])
-            sd, ss = select_top_k(d, imp if mode == nat.PT2_SUM else cpl, k, ham.n_orbitals)
+            d, sc, live = ws.select_head(ham if mode == nat.PT2_SUM else None, ns, energy, k)
+            uniq += live
+            sd, ss = select_top_k(d, sc, k, ham.n_orbitals)
             keep_d.append(sd.clone())
             keep_s.append(ss.clone())
-            del d, cpl, imp
+            del d, sc
         if ok:
             break
         n_pass *= 2

@@ -250,6 +250,20 @@ int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy, ui
                    double* out_coupling, double* out_diag, double* out_importance,
                    int64_t* n_live, void* stream);
 
+/* Streaming selection (what _find_important_configs' torch.topk, :551-552, needs): instead of
+ * exporting every candidate, fgk_pt2_score computes each live candidate's score in place --
+ * importance coupling^2 / (|energy - diag| + 1e-10) if h != NULL, else |coupling| -- counts
+ * scores per binary exponent in hist (device uint32[2048], scratch) and derives the bound
+ * thr (device uint64[2]: {lowest score bit pattern to keep, number kept}) that keeps at
+ * least k candidates plus one exponent bin of slack.  Synchronises; *n_live = live
+ * candidates, *n_keep = candidates at or above the bound (size the gather buffers with it).
+ * fgk_pt2_gather compacts those candidates (order unspecified) into out_dets / out_score;
+ * synchronises; FGK_ERR_CAPACITY if out_cap is too small. */
+int fgk_pt2_score(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double energy, int64_t k, uint32_t* hist,
+                  uint64_t* thr, int64_t* n_live, int64_t* n_keep, void* stream);
+int fgk_pt2_gather(fgk_pt2_t ws, int64_t n_slots, const uint64_t* thr, uint64_t* out_dets,
+                   double* out_score, int64_t out_cap, int64_t* n_written, void* stream);
+
 /* Dedup exchange helper: owner rank of a determinant = (hash >> 24) % world.
  * scatter = 0: cursors[w] += number of pairs owned by w (cursors zeroed by the caller);
  * scatter = 1: cursors[w] hold the segment starts (exclusive scan of the counts); pairs are

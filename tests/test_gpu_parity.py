@@ -575,6 +575,38 @@ def test_rank_builder_without_dense_pair_table(fgk):
     assert Q.nnz == A.nnz and float((Q.matvec(x) - y).abs().max()) < 1e-10
 
 
+def test_pt2_select_head_equals_full_topk(fgk):
+    """fgk_pt2_score / fgk_pt2_gather (score in place, exponent histogram, gather the head) followed
+    by the deterministic top-k must pick exactly what the top-k over the full export picks: for
+    k below / around / above the number of candidates, for the importance score and for max|c.H|."""
+    from flow_guided_krylov_b200.expansion import Pt2Workspace, select_top_k
+    g = load_golden("sci_beh2_wide")
+    H, O, n_orb = make_pair(fgk, g)
+    basis = g["r0_basis"]
+    E, v = float(g["r1_E"]), g["r1_v"]
+    dets = H.pack(t64(basis))
+    idx = fgk.BasisIndex(dets)
+    c32 = torch.from_numpy(v).cuda().float()
+    src = torch.nonzero(c32.abs() > 1e-8).squeeze(1)
+    for mode, ham in ((fgk.PT2_SUM, H), (fgk.PT2_MAXABS, None)):
+        ws = Pt2Workspace(1 << 16, "cuda:0")
+        ws.accumulate(H, idx, src, c32[src].double(), mode)
+        ns, raw, ov = ws.count()
+        assert not ov and ns > 100
+        d, cpl, _, imp = ws.export(H, ns, E)
+        full_score = imp if mode == fgk.PT2_SUM else cpl
+        n_live = d.shape[0]
+        for k in (1, 7, 50, n_live - 1, n_live, n_live + 10):
+            hd, hs, live = ws.select_head(ham, ns, E, k)
+            assert live == n_live and hd.shape[0] >= min(k, n_live)
+            a_d, a_s = select_top_k(hd, hs, k, n_orb)
+            b_d, b_s = select_top_k(d, full_score, k, n_orb)
+            assert torch.equal(a_d, b_d) and torch.equal(a_s, b_s)
+        # the head is a small part of the list when the scores span many binades
+        hd, _, _ = ws.select_head(ham, ns, E, 5)
+        assert hd.shape[0] < n_live
+
+
 def test_config5_shape_pt2_96_sites(fgk):
     """48 orbitals = 96 sites (beyond the reference's own 64-bit key):
     PT2 candidates, couplings and importances against the oracle, incl. the multi-pass path."""
