@@ -251,6 +251,31 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// <D|H|D> computed by a whole warp: lane p (and p + 32) takes orbital p's h_pp and nibble row
+// sums, then one butterfly sum.  In the row builders a single lane used to walk all occupied
+// orbitals (~200 dependent loads, 13 % of k_projh3's instructions, ncu r01r); every lane gets
+// the result.  Called convergently by all 32 lanes.
+__device__ __forceinline__ double warp_diag_element(const HamView& H, fgk_det d, int lane)
+{
+    LdgD ldd;
+    if (!H.nib_jk) {                    // n_orb > 56: pair-loop form on one lane
+        double e = 0.0;
+        if (lane == 0) e = diag_element_loops(H, d, ldd);
+        return __shfl_sync(0xffffffffu, e, 0);
+    }
+    const int n = H.n_orb, nc = H.nchunk;
+    double part = 0.0;
+    for (int p = lane; p < n; p += 32) {
+        const u64 bit = orb_bit(n, p);
+        if (d.a & bit)
+            part += ldd(H.hdiag + p) + 0.5 * nib_rowsum(H.nib_jk + (size_t)p * nc * 16, nc, d.a, ldd) +
+                    nib_rowsum(H.nib_jab + (size_t)p * nc * 16, nc, d.b, ldd);
+        if (d.b & bit)
+            part += ldd(H.hdiag + p) + 0.5 * nib_rowsum(H.nib_jk + (size_t)p * nc * 16, nc, d.b, ldd);
+    }
+    return H.e_nuc + warp_sum(part);
+}
+
 __device__ __forceinline__ i64 warp_sum_i64(i64 v)
 {
 #pragma unroll

@@ -23,7 +23,6 @@ k_projh(HamView H, IndexView I, i64 row_begin, i64 row_end, int mode, i64* __res
     const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
     const bool sym = (mode & FGK_H_SYM) != 0, drop0 = (mode & FGK_H_DROP_ZEROS) != 0;
     LdgF ldf;
-    LdgD ldd;
     for (i64 i = row_begin + warp0; i < row_end; i += nwarps) {
         ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + i);
         fgk_det d = {dv.x, dv.y};
@@ -31,9 +30,12 @@ k_projh(HamView H, IndexView I, i64 row_begin, i64 row_end, int mode, i64* __res
         warp_build_ctx(c, H.n_orb, d, s_lists[wib], lane);
         i64 pos = FILL ? row_ptr[i - row_begin] : 0;
         // diagonal first (always stored, like skqd.py:394-397)
-        if (FILL && lane == 0) {
-            cols[pos] = (int32_t)i;
-            vals[pos] = diag_element(H, d, ldd);
+        if (FILL) {
+            const double dg = warp_diag_element(H, d, lane);
+            if (lane == 0) {
+                cols[pos] = (int32_t)i;
+                vals[pos] = dg;
+            }
         }
         pos += 1;
         auto visit = [&](bool valid, const Excitation& x) {
@@ -112,7 +114,6 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
     const bool sym = (mode & FGK_H_SYM) != 0, drop0 = (mode & FGK_H_DROP_ZEROS) != 0;
     const int n = H.n_orb;
     LdgF ldf;
-    LdgD ldd;
     for (i64 i = row_begin + warp0; i < row_end; i += nwarps) {
         ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + i);
         fgk_det d = {dv.x, dv.y};
@@ -127,9 +128,12 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
             return slice_ptr ? row_base + (k >> 1) * 64 + (k & 1) : row_base + k;
         };
         i64 pos = 0;
-        if (FILL && lane == 0) {
-            cols[at(0)] = (int32_t)i;
-            vals[at(0)] = diag_element(H, d, ldd);
+        if (FILL) {
+            const double dg = warp_diag_element(H, d, lane);
+            if (lane == 0) {
+                cols[at(0)] = (int32_t)i;
+                vals[at(0)] = dg;
+            }
         }
         pos += 1;
         // full-key probe + element of one candidate per lane; rank inside the row by ballot.
@@ -278,8 +282,9 @@ k_projh2(HamView H, IndexView I, ProjLists PL, i64 row_begin, i64 row_end, int m
 // Requires the scan mode for both spins (fewer distinct strings than same-spin excitations
 // per row); otherwise fgk_projh_* fall back to k_projh2.
 struct __align__(8) SEntry {
-    unsigned short he;     // hole << 8 | particle
-    unsigned short par;    // bit0 pk, bit1 pb (alpha-beta factors), bit2 s1 ket, bit3 s1 bra
+    unsigned short offk;   // particle * n + hole  (ket-side table offset part, < 4096)
+    unsigned short offb;   // hole * n + particle  (bra side) | parities << 12:
+                           // bit12 pk, bit13 pb (alpha-beta factors), bit14 s1 ket, bit15 s1 bra
     int rank;              // rank of the target string
 };
 
@@ -300,7 +305,6 @@ k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_e
     const bool need_sign = FILL || drop0;
     const int n = H.n_orb, n2 = n * n;
     const int nbs = (int)I.n_bstr;
-    LdgD ldd;
     for (i64 i = row_begin + warp0; i < row_end; i += nwarps) {
         const ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + i);
         const fgk_det d = {dv.x, dv.y};
@@ -312,9 +316,12 @@ k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_e
             return slice_ptr ? row_base + (k >> 1) * 64 + (k & 1) : row_base + k;
         };
         i64 pos = 0;
-        if (FILL && lane == 0) {
-            cols[at(0)] = (int32_t)i;
-            vals[at(0)] = diag_element(H, d, ldd);
+        if (FILL) {
+            const double dg = warp_diag_element(H, d, lane);
+            if (lane == 0) {
+                cols[at(0)] = (int32_t)i;
+                vals[at(0)] = dg;
+            }
         }
         pos += 1;
         // column of (alpha rank, beta rank), or -1
@@ -396,8 +403,8 @@ k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_e
                     const int o = cnt + __popc(bs & lt);
                     if (o < cap) {
                         SEntry e;
-                        e.he = (unsigned short)((hh << 8) | ee);
-                        e.par = (unsigned short)(pk | (pb << 1) | (sk << 2) | (sb << 3));
+                        e.offk = (unsigned short)(ee * n + hh);
+                        e.offb = (unsigned short)((hh * n + ee) | ((pk | (pb << 1) | (sk << 2) | (sb << 3)) << 12));
                         e.rank = t;
                         L[o] = e;
                     }
@@ -432,11 +439,10 @@ k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_e
                     const SEntry e = L[t];
                     j = spin ? column(ia, e.rank) : column(e.rank, ib);
                     if (j >= 0) {
-                        const int hh = e.he >> 8, ee = e.he & 0xff;
-                        rb_ = __ldg(H.h1 + hh * n + ee);
-                        if (sym) rk = __ldg(H.h1 + ee * n + hh);
-                        park = (e.par >> 2) & 1;
-                        parb = (e.par >> 3) & 1;
+                        rb_ = __ldg(H.h1 + (e.offb & 0xfff));
+                        if (sym) rk = __ldg(H.h1 + e.offk);
+                        park = (e.offb >> 14) & 1;
+                        parb = (e.offb >> 15) & 1;
                     }
                 }
                 emit(j >= 0, j, rb_, rk, parb, park);
@@ -446,20 +452,24 @@ k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_e
         const int nsa = n_single[0], nsb = n_single[1], total = nsa * nsb;
         const SEntry* La = s_single;
         const SEntry* Lb = s_single + cap;
+        const float inv_nsb = nsb ? 1.0f / (float)nsb : 0.f;
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
             int j = -1, parb = 0, park = 0;
             float rb_ = 0.f, rk = 0.f;
             if (t < total) {
-                const int ka = t / nsb, kb = t - ka * nsb;
+                // t -> (ka, kb): float reciprocal + one-step fix-up (t < 2^20) instead of an integer division
+                int ka = (int)((float)t * inv_nsb), kb = t - ka * nsb;
+                if (kb < 0) { ka--; kb += nsb; }
+                else if (kb >= nsb) { ka++; kb -= nsb; }
                 const SEntry ea = La[ka], eb = Lb[kb];
                 j = column(ea.rank, eb.rank);
                 if (j >= 0) {
-                    const int h0 = ea.he >> 8, e0 = ea.he & 0xff, h1 = eb.he >> 8, e1 = eb.he & 0xff;
-                    rb_ = __ldg(H.g + (h0 * n + e0) * n2 + h1 * n + e1);
-                    if (sym) rk = __ldg(H.g + (e0 * n + h0) * n2 + e1 * n + h1);
-                    park = (ea.par ^ eb.par ^ 1) & 1;
-                    parb = ((ea.par ^ eb.par) >> 1 ^ 1) & 1;
+                    rb_ = __ldg(H.g + (ea.offb & 0xfff) * n2 + (eb.offb & 0xfff));
+                    if (sym) rk = __ldg(H.g + ea.offk * n2 + eb.offk);
+                    const unsigned px = (unsigned)(ea.offb ^ eb.offb);
+                    park = ((px >> 12) ^ 1) & 1;
+                    parb = ((px >> 13) ^ 1) & 1;
                 }
             }
             emit(j >= 0, j, rb_, rk, parb, park);
