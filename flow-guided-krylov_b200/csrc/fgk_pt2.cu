@@ -179,6 +179,150 @@ k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_
     if (lane == 0 && tested) atomicAdd(W.counters + 1, (unsigned long long)tested);
 }
 
+// ---- accumulate, second form: buckets by the candidate's ALPHA STRING -----------------------
+// The bucket of a candidate (pass of a multi-pass sweep, owner rank of a sharded sweep) is
+// two-level, n_pass = n_a * n_d: first (word_hash(alpha') >> 40) % n_a on its alpha string,
+// then (det_hash >> 40) % n_d on the full key (n_d = 1 up to 64 buckets; the second level only
+// exists so that very many passes still split a single alpha string's candidates).  Whole runs
+// of the walk share the first-level bucket and are skipped before any per-candidate work:
+//   beta singles, beta-beta doubles : alpha' = the source's alpha  -> all or nothing per source
+//   alpha-beta doubles (70 % of the connections): alpha' is fixed by the alpha single, so the
+//     loop runs over (alpha single) x (chunks of beta singles) and skips foreign alpha singles
+//   alpha singles, alpha-alpha doubles : one word hash per candidate
+// With per-candidate buckets every rank / pass paid the full walk (decode, table value, parity,
+// 128-bit hash) for every connection, owned or not.  As in k_projh3 the alpha-beta table offset
+// and sign parity split into per-single parts, precomputed once per work unit in shared memory:
+// entry = hole | particle << 8 | pk << 16 | s1 << 17 | owned << 18.
+template <int BPS>
+__global__ void __launch_bounds__(FGK_BLOCK, BPS)
+k_pt2_accumulate2(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_idx,
+                  const double* __restrict__ coeff, i64 n_src, int n_split, int mode, unsigned n_a,
+                  unsigned a_id, unsigned n_d, unsigned d_id, int cap)
+{
+    extern __shared__ __align__(16) unsigned s_ent[];           // [warps][2][cap]
+    __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
+    const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
+    const i64 n_units = n_src * n_split;
+    const int n = H.n_orb, n2 = n * n;
+    unsigned* const La = s_ent + (size_t)wib * 2 * cap;
+    unsigned* const Lb = La + cap;
+    LdgF ldf;
+    i64 tested = 0;
+    auto mine = [&](u64 alpha_word) -> bool {
+        return n_a <= 1 || (unsigned)((word_hash(alpha_word) >> 40) % n_a) == a_id;
+    };
+    for (i64 unit = warp0; unit < n_units; unit += nwarps) {
+        const i64 sidx = unit / n_split;
+        const int split = (int)(unit - sidx * n_split);
+        const i64 j = __ldg(src_idx + sidx);
+        const double cj = __ldg(coeff + sidx);
+        const ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(I.dets) + j);
+        const fgk_det d = {dv.x, dv.y};
+        DetCtx c;
+        warp_build_ctx(c, n, d, s_lists[wib], lane);
+        const int nsa = c.noa * c.nva, nsb = c.nob * c.nvb;
+        // singles lists: every (occupied, virtual) pair, reference order (hole-major)
+        for (int spin = 0; spin < 2; spin++) {
+            const u64 w = spin ? d.b : d.a;
+            const uint8_t* occ = spin ? c.occ_b : c.occ_a;
+            const uint8_t* virt = spin ? c.virt_b : c.virt_a;
+            const int nv = spin ? c.nvb : c.nva, ns = spin ? nsb : nsa;
+            unsigned* L = spin ? Lb : La;
+            for (int t = lane; t < ns; t += 32) {
+                const int hh = occ[t / nv], ee = virt[t % nv];
+                const unsigned pk = (unsigned)(__popcll(w & span_mask(n, ee, hh)) + (ee < hh)) & 1u;
+                const unsigned s1 = (unsigned)sign1_parity(w, n, ee, hh);
+                unsigned own = 1u;
+                if (!spin) own = mine(w ^ orb_bit(n, hh) ^ orb_bit(n, ee)) ? 1u : 0u;
+                L[t] = (unsigned)hh | ((unsigned)ee << 8) | (pk << 16) | (s1 << 17) | (own << 18);
+            }
+        }
+        __syncwarp();
+        const bool own_src = mine(d.a);
+        // candidate o with value el (already filtered): count, drop basis members, accumulate
+        auto push_candidate = [&](bool push, fgk_det o, float el, int cls) {
+            if (push) {
+                const u64 h = det_hash(o.a, o.b);
+                if (n_d > 1 && (unsigned)((h >> 40) % n_d) != d_id) return;
+                tested++;
+                if (index_find_filtered_h(I, o, h, cls) < 0) pt2_upsert(W, o, h, cj * (double)el, mode);
+            }
+        };
+        // chunk space: [alpha singles][beta singles][aa][bb][alpha single x beta-single chunks]
+        const int cbk = (nsb + 31) >> 5;
+        const int g0 = (nsa + 31) >> 5;
+        const int g1 = g0 + cbk;
+        const int g2 = g1 + ((c.n_aa + 31) >> 5);
+        const int g3 = g2 + ((c.n_bb + 31) >> 5);
+        const int g4 = g3 + nsa * cbk;
+        for (int g = split; g < g4; g += n_split) {
+            if (g < g1) {                                   // singles
+                const bool beta = g >= g0;
+                if (beta && !own_src) continue;
+                const int t = (beta ? g - g0 : g) * 32 + lane;
+                const int ns = beta ? nsb : nsa;
+                bool push = false;
+                float el = 0.f;
+                fgk_det o = d;
+                if (t < ns) {
+                    const unsigned e = beta ? Lb[t] : La[t];
+                    const int hh = e & 0xff, ee = (e >> 8) & 0xff;
+                    if ((e >> 18) & 1u) {
+                        const float v = ldf(H.h1 + ee * n + hh);            // molecular.py:234-251
+                        if (fabsf(v) > 1e-12f) {
+                            push = true;
+                            el = ((e >> 17) & 1u) ? -v : v;
+                            const u64 flip = orb_bit(n, hh) ^ orb_bit(n, ee);
+                            if (beta) o.b ^= flip; else o.a ^= flip;
+                        }
+                    }
+                }
+                push_candidate(push, o, el, beta ? 1 : 0);
+            } else if (g < g3) {                            // same-spin doubles
+                const int st = g < g2 ? 2 : 3;
+                if (st == 3 && !own_src) continue;
+                const int size = st == 2 ? c.n_aa : c.n_bb;
+                const int t = (g - (st == 2 ? g1 : g2)) * 32 + lane;
+                bool push = false;
+                float el = 0.f;
+                fgk_det o = d;
+                if (t < size) {
+                    Excitation x;
+                    decode_double(c, st, t, x);
+                    o = apply_excitation(d, n, x);
+                    if (st == 3 || mine(o.a)) push = ket_element_fast(H, d, x, ldf, el);
+                }
+                push_candidate(push, o, el, st);
+            } else {                                        // alpha-beta doubles
+                const int gg = g - g3;
+                const int ka = gg / cbk, kb = (gg - ka * cbk) * 32 + lane;
+                const unsigned ea = La[ka];
+                if (!((ea >> 18) & 1u)) continue;           // alpha' belongs to another bucket
+                bool push = false;
+                float el = 0.f;
+                fgk_det o = d;
+                if (kb < nsb) {
+                    const unsigned eb = Lb[kb];
+                    const int h0 = ea & 0xff, e0 = (ea >> 8) & 0xff, h1 = eb & 0xff, e1 = (eb >> 8) & 0xff;
+                    const float v = ldf(H.g + (e0 * n + h0) * n2 + e1 * n + h1);   // molecular.py:302-318
+                    if (fabsf(v) > 1e-12f) {
+                        push = true;
+                        el = (((ea ^ eb) >> 16) & 1u) ? v : -v;               // parity = pk_a ^ pk_b ^ 1
+                        o.a ^= orb_bit(n, h0) ^ orb_bit(n, e0);
+                        o.b ^= orb_bit(n, h1) ^ orb_bit(n, e1);
+                    }
+                }
+                push_candidate(push, o, el, 4);
+            }
+        }
+        __syncwarp();
+    }
+    tested = warp_sum_i64(tested);
+    if (lane == 0 && tested) atomicAdd(W.counters + 1, (unsigned long long)tested);
+}
+
 __global__ void __launch_bounds__(256)
 k_pt2_merge(Pt2View W, const fgk_det* __restrict__ dets, const double* __restrict__ vals, i64 m, int mode)
 {
@@ -541,9 +685,31 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
         FGK_CUDA(cudaMemsetAsync(ws->v.qcursors, 0, sizeof(unsigned long long) << ws->v.queue_bits,
                                  (cudaStream_t)stream));
     }
-    else if (bps == 8) FGK_PT2_LAUNCH(8, false);
-    else if (bps == 6) FGK_PT2_LAUNCH(6, false);
-    else FGK_PT2_LAUNCH(4, false);
+    else {
+        const int n = h->v.n_orb, na = h->v.n_alpha, nb = h->v.n_beta;
+        int scap = na * (n - na) > nb * (n - nb) ? na * (n - na) : nb * (n - nb);
+        if (scap < 1) scap = 1;
+        const size_t smem = sizeof(unsigned) * 2 * (size_t)scap * FGK_WARPS_PER_BLOCK;
+        static const bool per_candidate = getenv("FGK_PT2_PER_CANDIDATE_BUCKETS") != nullptr;
+        if (!per_candidate) {
+            // buckets by alpha string (see k_pt2_accumulate2)
+            if (smem > 40 * 1024)
+                FGK_CUDA(cudaFuncSetAttribute(k_pt2_accumulate2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            unsigned n_a = (unsigned)n_pass;                 // first level: largest divisor <= 64
+            if (n_a > 64) {
+                n_a = 1;
+                for (unsigned dv = 64; dv >= 2; dv--)
+                    if ((unsigned)n_pass % dv == 0) { n_a = dv; break; }
+            }
+            const unsigned n_d = (unsigned)n_pass / n_a;
+            k_pt2_accumulate2<4><<<grid, FGK_BLOCK, smem, (cudaStream_t)stream>>>(
+                h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, n_a,
+                (unsigned)pass_id % n_a, n_d, (unsigned)pass_id / n_a, scap);
+        }
+        else if (bps == 8) FGK_PT2_LAUNCH(8, false);
+        else if (bps == 6) FGK_PT2_LAUNCH(6, false);
+        else FGK_PT2_LAUNCH(4, false);
+    }
 #undef FGK_PT2_LAUNCH
     FGK_LAUNCH_CHECK();
     return FGK_OK;

@@ -229,9 +229,12 @@ int fgk_pt2_reset(fgk_pt2_t ws, void* stream);
 /* For every source s in [0,n_src): j = src_idx[s] (basis position), coefficient
  * coeff[s]; every connection x of basis[j] with x not in the basis adds
  * coeff[s]*<x|H|j> to x's accumulator (mode SUM) or maxes |.| (mode MAXABS).
- * Only candidates with (hash(x) >> 40) % n_pass == pass_id are handled, so that a
- * candidate set larger than the workspace can be processed exactly in n_pass
- * sweeps.  Overflow is reported by fgk_pt2_count. */
+ * Only the candidates of bucket pass_id out of n_pass are handled, so that a candidate set
+ * larger than the workspace can be processed exactly in n_pass sweeps (and N ranks can own
+ * disjoint buckets).  Buckets partition the candidate space: by a hash of the candidate's
+ * alpha string (up to 64 buckets; runs of connections that share an alpha string are skipped
+ * as a whole), refined by a hash of the full determinant beyond that.  Overflow is reported
+ * by fgk_pt2_count. */
 int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, const int64_t* src_idx,
                        const double* coeff, int64_t n_src, int mode, int n_pass, int pass_id,
                        void* stream);
