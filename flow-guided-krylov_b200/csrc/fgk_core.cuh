@@ -451,6 +451,24 @@ FGK_HD int exc_parity_ket(fgk_det ket, int n, const Excitation& x)
     }
 }
 
+// ---- separable form of the alpha-beta double excitation -------------------------------------
+// For a+_p a+_r a_s a_q with (q -> p) in the alpha and (s -> r) in the beta block, both the
+// table offset and the reference's sign parity split into one factor per single excitation:
+//   g[p,q,r,s]          = g[(p n + q) n^2 + (r n + s)]
+//   parity (ket side)   = pk_alpha ^ pk_beta ^ 1,  pk = popc(word & span(e,h)) + [e < h]
+//   parity (bra side)   = pb_alpha ^ pb_beta ^ 1,  pb = popc(word' & span(h,e)) + [h < e]
+// (word' = word with the single applied; exc_parity_ket, class 4).  sk / sb are the single's
+// own parities on the ket / bra side (class 0 / 1).  Used by k_projh3 and k_pt2_accumulate2,
+// verified against the generic forms by fgk_hostcheck (hc_bra_row3, hc_pt2_walk2).
+FGK_HD void single_factors(u64 w, u64 w2, int n, int hh, int ee, unsigned& pk, unsigned& pb,
+                           unsigned& sk, unsigned& sb)
+{
+    pk = (unsigned)(fgk_popc(w & span_mask(n, ee, hh)) + (ee < hh)) & 1u;
+    pb = (unsigned)(fgk_popc(w2 & span_mask(n, hh, ee)) + (hh < ee)) & 1u;
+    sk = (unsigned)sign1_parity(w, n, ee, hh);
+    sb = (unsigned)sign1_parity(w2, n, hh, ee);
+}
+
 // <D|H|D+x> as get_connections(D+x) reports it: roles reversed on the ket D+x
 FGK_HD int exc_parity_bra(fgk_det bra, int n, const Excitation& x)
 {

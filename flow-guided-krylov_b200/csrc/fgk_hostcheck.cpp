@@ -6,6 +6,7 @@
 // oracle on a machine without a GPU.  Built by tests with plain g++.
 #include <map>
 #include <utility>
+#include <vector>
 #include "fgk_core.cuh"
 #include "fgk_tables.h"
 
@@ -207,6 +208,144 @@ long hc_bra_row2(void* h, const u64* basis, long n, long i, int mode, int scan, 
         for (auto& b : L[1]) {
             Excitation e; e.cls = 4; e.h0 = a.first; e.e0 = a.second; e.h1 = b.first; e.e1 = b.second;
             emit(e);
+        }
+    return m;
+}
+
+// Rank-based bra-mode row (the k_projh3 strategy): sorted distinct-string lists are scanned,
+// singles become entries {offk, offb, parity factors, rank}, the column comes from the
+// (alpha rank, beta rank) pair map, alpha-beta values and signs from the separable form.
+long hc_bra_row3(void* h, const u64* basis, long n, long i, int mode, int* out_cols, double* out_vals,
+                 long cap)
+{
+    HcHam* H = (HcHam*)h;
+    const HamView& V = H->V;
+    const int nn = V.n_orb, n2 = nn * nn;
+    std::map<u64, int> arank, brank;
+    for (long k = 0; k < n; k++) { arank[basis[2 * k]] = 0; brank[basis[2 * k + 1]] = 0; }
+    std::vector<u64> alist, blist;
+    for (auto& kv : arank) { kv.second = (int)alist.size(); alist.push_back(kv.first); }
+    for (auto& kv : brank) { kv.second = (int)blist.size(); blist.push_back(kv.first); }
+    std::map<std::pair<int, int>, long> pair;
+    for (long k = 0; k < n; k++) pair[{arank[basis[2 * k]], brank[basis[2 * k + 1]]}] = k;   // last index wins
+    fgk_det d = {basis[2 * i], basis[2 * i + 1]};
+    const int ia = arank[d.a], ib = brank[d.b];
+    const bool sym = mode == 1;
+    long m = 0;
+    if (m < cap) { out_cols[m] = (int)i; out_vals[m] = diag_element(V, d, ldd_host); }
+    m++;
+    auto column = [&](int ra, int rb) -> long {
+        auto it = pair.find({ra, rb});
+        return it == pair.end() ? -1 : it->second;
+    };
+    auto emit = [&](long j, float rb_, float rk, unsigned parb, unsigned park) {
+        if (j < 0) return;
+        const bool kij = (rb_ < 0 ? -rb_ : rb_) > 1e-12f;
+        const bool kji = sym && (rk < 0 ? -rk : rk) > 1e-12f;
+        if (!kij && !kji) return;
+        const float vij = kij ? (parb ? -rb_ : rb_) : 0.f;
+        const float vji = kji ? (park ? -rk : rk) : 0.f;
+        const double v = sym ? 0.5 * ((double)vij + (double)vji) : (double)vij;
+        if (m < cap) { out_cols[m] = (int)j; out_vals[m] = v; }
+        m++;
+    };
+    struct Ent { int offk, offb; unsigned pk, pb, sk, sb; int rank; };
+    std::vector<Ent> L[2];
+    for (int spin = 0; spin < 2; spin++) {
+        const u64 w = spin ? d.b : d.a;
+        const std::vector<u64>& list = spin ? blist : alist;
+        for (int t = 0; t < (int)list.size(); t++) {
+            const u64 w2 = list[t];
+            const int pc = fgk_popc(w2 ^ w);
+            if (pc == 2) {
+                int hh, ee;
+                single_from_strings(w, w2, nn, hh, ee);
+                Ent e;
+                single_factors(w, w2, nn, hh, ee, e.pk, e.pb, e.sk, e.sb);
+                e.offk = ee * nn + hh; e.offb = hh * nn + ee; e.rank = t;
+                L[spin].push_back(e);
+            } else if (pc == 4) {
+                const long j = spin ? column(ia, t) : column(t, ib);
+                int h0, h1, e0, e1;
+                double_from_strings(w, w2, nn, h0, h1, e0, e1);
+                const float rb_ = V.w[((h0 * nn + e0) * nn + h1) * nn + e1];
+                const float rk = sym ? V.w[((e0 * nn + h0) * nn + e1) * nn + h1] : 0.f;
+                Excitation x, rx;
+                x.cls = rx.cls = 2;
+                x.h0 = h0; x.h1 = h1; x.e0 = e0; x.e1 = e1;
+                rx.h0 = e0; rx.h1 = e1; rx.e0 = h0; rx.e1 = h1;
+                const fgk_det kd = {w, 0}, ko = {w2, 0};
+                emit(j, rb_, rk, (unsigned)exc_parity_ket(ko, nn, rx), (unsigned)exc_parity_ket(kd, nn, x));
+            }
+        }
+    }
+    for (int spin = 0; spin < 2; spin++)
+        for (auto& e : L[spin])
+            emit(spin ? column(ia, e.rank) : column(e.rank, ib), V.h1[e.offb], sym ? V.h1[e.offk] : 0.f, e.sb, e.sk);
+    for (auto& a : L[0])
+        for (auto& b : L[1])
+            emit(column(a.rank, b.rank), V.g[a.offb * n2 + b.offb], sym ? V.g[a.offk * n2 + b.offk] : 0.f,
+                 a.pb ^ b.pb ^ 1u, a.pk ^ b.pk ^ 1u);
+    return m;
+}
+
+// The PT2 walk of k_pt2_accumulate2 (one bucket): singles lists over every (occupied, virtual)
+// pair, alpha-beta candidates from the separable form, same-spin doubles by decode_double.
+// Emits (candidate, element) in the kernel's chunk order; the set must equal hc_connections'.
+long hc_pt2_walk2(void* h, u64 a, u64 b, u64* out_dets, float* out_el, long cap)
+{
+    HcHam* H = (HcHam*)h;
+    const HamView& V = H->V;
+    const int nn = V.n_orb, n2 = nn * nn;
+    uint8_t buf[256];
+    DetCtx c;
+    fgk_det d = {a, b};
+    detctx_fill_host(c, nn, d, buf);
+    long m = 0;
+    auto put = [&](fgk_det o, float el) {
+        if (m < cap) { out_dets[2 * m] = o.a; out_dets[2 * m + 1] = o.b; out_el[m] = el; }
+        m++;
+    };
+    struct Ent { int hh, ee; unsigned pk, s1; };
+    std::vector<Ent> L[2];
+    for (int spin = 0; spin < 2; spin++) {
+        const u64 w = spin ? d.b : d.a;
+        const uint8_t* occ = spin ? c.occ_b : c.occ_a;
+        const uint8_t* virt = spin ? c.virt_b : c.virt_a;
+        const int nv = spin ? c.nvb : c.nva, ns = (spin ? c.nob : c.noa) * nv;
+        for (int t = 0; t < ns; t++) {
+            Ent e;
+            e.hh = occ[t / nv]; e.ee = virt[t % nv];
+            unsigned pb, sb;
+            single_factors(w, w ^ orb_bit(nn, e.hh) ^ orb_bit(nn, e.ee), nn, e.hh, e.ee, e.pk, pb, e.s1, sb);
+            L[spin].push_back(e);
+        }
+    }
+    for (int spin = 0; spin < 2; spin++)
+        for (auto& e : L[spin]) {
+            const float v = V.h1[e.ee * nn + e.hh];
+            if (!((v < 0 ? -v : v) > 1e-12f)) continue;
+            fgk_det o = d;
+            const u64 flip = orb_bit(nn, e.hh) ^ orb_bit(nn, e.ee);
+            if (spin) o.b ^= flip; else o.a ^= flip;
+            put(o, e.s1 ? -v : v);
+        }
+    const int sizes[2] = {c.n_aa, c.n_bb};
+    for (int st = 2; st <= 3; st++)
+        for (int t = 0; t < sizes[st - 2]; t++) {
+            Excitation x;
+            decode_double(c, st, t, x);
+            float el;
+            if (ket_element_fast(V, d, x, ldf_host, el)) put(apply_excitation(d, nn, x), el);
+        }
+    for (auto& ea : L[0])
+        for (auto& eb : L[1]) {
+            const float v = V.g[(ea.ee * nn + ea.hh) * n2 + eb.ee * nn + eb.hh];
+            if (!((v < 0 ? -v : v) > 1e-12f)) continue;
+            fgk_det o = d;
+            o.a ^= orb_bit(nn, ea.hh) ^ orb_bit(nn, ea.ee);
+            o.b ^= orb_bit(nn, eb.hh) ^ orb_bit(nn, eb.ee);
+            put(o, ((ea.pk ^ eb.pk) & 1u) ? v : -v);
         }
     return m;
 }

@@ -397,9 +397,8 @@ k_projh3(HamView H, IndexView I, ProjLists PL, int cap, i64 row_begin, i64 row_e
                 if (pc == 2) {
                     int hh, ee;
                     single_from_strings(w, w2, n, hh, ee);
-                    const int pk = (__popcll(w & span_mask(n, ee, hh)) + (ee < hh)) & 1;
-                    const int pb = (__popcll(w2 & span_mask(n, hh, ee)) + (hh < ee)) & 1;
-                    const int sk = sign1_parity(w, n, ee, hh), sb = sign1_parity(w2, n, hh, ee);
+                    unsigned pk, pb, sk, sb;
+                    single_factors(w, w2, n, hh, ee, pk, pb, sk, sb);
                     const int o = cnt + __popc(bs & lt);
                     if (o < cap) {
                         SEntry e;

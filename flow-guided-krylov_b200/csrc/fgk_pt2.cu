@@ -232,10 +232,11 @@ k_pt2_accumulate2(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src
             unsigned* L = spin ? Lb : La;
             for (int t = lane; t < ns; t += 32) {
                 const int hh = occ[t / nv], ee = virt[t % nv];
-                const unsigned pk = (unsigned)(__popcll(w & span_mask(n, ee, hh)) + (ee < hh)) & 1u;
-                const unsigned s1 = (unsigned)sign1_parity(w, n, ee, hh);
+                const u64 w2 = w ^ orb_bit(n, hh) ^ orb_bit(n, ee);
+                unsigned pk, pb, s1, sb;
+                single_factors(w, w2, n, hh, ee, pk, pb, s1, sb);
                 unsigned own = 1u;
-                if (!spin) own = mine(w ^ orb_bit(n, hh) ^ orb_bit(n, ee)) ? 1u : 0u;
+                if (!spin) own = mine(w2) ? 1u : 0u;
                 L[t] = (unsigned)hh | ((unsigned)ee << 8) | (pk << 16) | (s1 << 17) | (own << 18);
             }
         }

@@ -73,6 +73,10 @@ def hostcheck():
         L.hc_bra_row.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64]
         L.hc_bra_row2.restype = i64
         L.hc_bra_row2.argtypes = [vp, vp, i64, i64, ci, ci, vp, vp, i64]
+        L.hc_bra_row3.restype = i64
+        L.hc_bra_row3.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64]
+        L.hc_pt2_walk2.restype = i64
+        L.hc_pt2_walk2.argtypes = [vp, u64, u64, vp, vp, i64]
         L.hc_check_split.restype = i64
         L.hc_check_split.argtypes = [vp, vp, i64]
         _hc = L

@@ -128,6 +128,51 @@ def test_structured_bra_rows_equal_flat_enumeration(name, mode, scan):
     hostcheck().hc_ham_destroy(hc)
 
 
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rank_based_bra_rows_equal_flat_enumeration(name, mode):
+    """the rank-based row builder (k_projh3 strategy: sorted string lists, pair map, separable
+    alpha-beta offsets and parities) produces exactly the entries of the flat enumeration"""
+    g = load_golden("ham_" + name)
+    hc, H, n_orb = make(g)
+    basis = np.unique(np.concatenate([g["basis"], g["dets"]]), axis=0)
+    pk = pack_np(basis, n_orb)
+    n = len(basis)
+    for i in range(0, n, max(1, n // 25)):
+        cap = n + 4
+        c1, v1 = np.zeros(cap, np.int32), np.zeros(cap)
+        c3, v3 = np.zeros(cap, np.int32), np.zeros(cap)
+        m1 = hostcheck().hc_bra_row(hc, _p(pk), n, i, mode, _p(c1), _p(v1), cap)
+        m3 = hostcheck().hc_bra_row3(hc, _p(pk), n, i, mode, _p(c3), _p(v3), cap)
+        assert m1 == m3
+        o1, o3 = np.argsort(c1[:m1], kind="stable"), np.argsort(c3[:m3], kind="stable")
+        assert np.array_equal(c1[:m1][o1], c3[:m3][o3])
+        assert np.array_equal(v1[:m1][o1].view(np.uint64), v3[:m3][o3].view(np.uint64))
+    hostcheck().hc_ham_destroy(hc)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pt2_walk_by_singles_lists_equals_reference_connections(name):
+    """the PT2 walk of k_pt2_accumulate2 (singles lists, separable alpha-beta elements) emits
+    exactly the reference's connections with exactly its float32 elements, in another order"""
+    g = load_golden("ham_" + name)
+    hc, _, n_orb = make(g)
+    offs = g["conn_offsets"]
+    pk = pack_np(g["dets"], n_orb)
+    for j in range(len(pk)):
+        cap = int(offs[j + 1] - offs[j]) + 8
+        od, oe = np.zeros((cap, 2), np.uint64), np.zeros(cap, np.float32)
+        m = hostcheck().hc_pt2_walk2(hc, int(pk[j, 0]), int(pk[j, 1]), _p(od), _p(oe), cap)
+        assert m == offs[j + 1] - offs[j]
+        ref = pack_np(g["conn_cfgs"][offs[j]:offs[j + 1]], n_orb)
+        ref_el = g["conn_elems"][offs[j]:offs[j + 1]].view(np.uint32)
+        o_got = np.lexsort((od[:m, 1], od[:m, 0]))
+        o_ref = np.lexsort((ref[:, 1], ref[:, 0]))
+        assert np.array_equal(od[:m][o_got], ref[o_ref])
+        assert np.array_equal(oe[:m].view(np.uint32)[o_got], ref_el[o_ref])
+    hostcheck().hc_ham_destroy(hc)
+
+
 def test_64_orbitals_bit63_edges():
     """n_orb = 64 uses every bit of both words (shift-by-64 hazards, sign bit)."""
     from helpers import synth_integrals
@@ -212,13 +257,15 @@ def test_random_shapes_against_oracle(seed):
     n = len(dets)
     D = H.dense_H(dets)
     for mode, ref in ((0, D), (1, 0.5 * (D + D.T))):
-        for builder in (0, 1, 2):
+        for builder in (0, 1, 2, 3):
             got = np.zeros_like(D)
             for i in range(n):
                 cap = n + 4
                 c, v = np.zeros(cap, np.int32), np.zeros(cap)
                 if builder == 0:
                     m = hostcheck().hc_bra_row(hc, _p(pk), n, i, mode, _p(c), _p(v), cap)
+                elif builder == 3:
+                    m = hostcheck().hc_bra_row3(hc, _p(pk), n, i, mode, _p(c), _p(v), cap)
                 else:
                     m = hostcheck().hc_bra_row2(hc, _p(pk), n, i, mode, builder - 1, _p(c), _p(v), cap)
                 got[i, c[:m]] = v[:m]
