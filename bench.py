@@ -340,6 +340,7 @@ def run_ours(args):
         tt[0] = nn[0]
     nnz_total, build_ms, cold_ms = float(tt[0]), float(tt[1]), float(tt[2])
     build = {"value": nnz_total / (build_ms * 1e-3), "unit": "H nnz built/s", "ms": build_ms,
+             "hbm_equivalent_GBs": 12.0 * nnz_total / (build_ms * 1e-3) / 1e9,      # 12 B written per nnz
              "cold_ms": cold_ms, "what": "index + count + scan + fill + SELL-32 copy; ms = second build "
              "(allocator warm), cold_ms = first build incl. cold cudaMalloc of the matrix buffers",
              "index_ms": t_index, "count_fill_ms": t_build, "sort_ms": t_sort, "to_sell_ms": t_sell,
@@ -540,6 +541,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
         pt2 = {"value": st["raw_candidates_total"] / (float(pms[0]) * 1e-3), "unit": "PT2 candidates/s",
+               "hbm_equivalent_GBs": 48.0 * st["raw_candidates_total"] / (float(pms[0]) * 1e-3) / 1e9,
                "raw_candidates": st["raw_candidates_total"], "sources": ns, "ms": float(pms[0]),
                "passes": st["passes"], "selected": int(sel.shape[0]),
                "unique_candidates": st["unique_total"], "partition": getattr(wsp, "partition", None),
