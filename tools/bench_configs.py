@@ -15,7 +15,10 @@ sys.path.insert(0, ROOT)
 import flow_guided_krylov_b200 as fgk  # noqa: E402
 from bench import synth_integrals  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
+from flow_guided_krylov_b200 import sto3g  # noqa: E402
 
+REAL = "--real" in sys.argv      # real STO-3G integrals from the PySCF-free front-end (sto3g.py)
+GEOM = {"lih": sto3g.lih_geometry, "beh2": sto3g.beh2_geometry, "n2": sto3g.n2_geometry}
 SHAPES = {"lih": (6, 2, 2), "beh2": (7, 3, 3), "n2": (10, 7, 7)}
 
 
@@ -25,13 +28,17 @@ def sync():
 
 def main():
     ref = {}
-    p = os.path.join(ROOT, "profiles", "ref_cpu_timings.json")
+    p = os.path.join(ROOT, "profiles", "ref_cpu_timings_sto3g.json" if REAL else "ref_cpu_timings.json")
     if os.path.exists(p):
         ref = json.load(open(p))["configs"]
     for name, (n, na, nb) in SHAPES.items():
-        h1, g = synth_integrals(n, seed=0)
-        H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, g, 0.0, na + nb, n, na, nb), "cuda:0")
-        O = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), na, nb)
+        if REAL:
+            I = sto3g.compute_molecular_integrals(GEOM[name]())
+            h1, g, e_nuc = I.h1e, I.h2e, I.nuclear_repulsion
+        else:
+            (h1, g), e_nuc = synth_integrals(n, seed=0), 0.0
+        H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, g, e_nuc, na + nb, n, na, nb), "cuda:0")
+        O = orc.OracleHam(h1.astype(np.float32), g.astype(np.float32), na, nb, e_nuc)
         k = {"lih": 150, "beh2": 200, "n2": 300}[name]
         ex = fgk.SelectedCIExpander(H, fgk.ResidualExpansionConfig(max_configs_per_iter=k))
         r = {}
@@ -83,7 +90,8 @@ def main():
             # Stage-3 energies vs the raw float32 reference: float32 envelope
             r["reference_energy_max_abs_diff"] = float(
                 np.abs(np.array(rr["expand_basis_energies"]) - np.array(energies)).max())
-        print(json.dumps({"config": name, "shape": [n, na, nb], **r}), flush=True)
+        print(json.dumps({"config": name, "shape": [n, na, nb],
+                          "integrals": "STO-3G" if REAL else "synthetic", **r}), flush=True)
 
 
 if __name__ == "__main__":
