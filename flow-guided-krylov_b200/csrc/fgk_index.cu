@@ -16,6 +16,24 @@
 
 #include "fgk_internal.cuh"
 
+// The index owns ~10 small device buffers.  Plain cudaMalloc / cudaFree calls get slow (tens of
+// ms per index on some boxes) once a caching allocator holds most of the device, and an index is
+// rebuilt for every new basis; the stream-ordered allocator with an unbounded release threshold
+// keeps the blocks in the device's default pool instead.
+static cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st, int device)
+{
+    static bool configured[64] = {false};
+    if (!configured[device & 63]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured[device & 63] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 16, st);
+}
+
 static u64 pow2_at_least(u64 x)
 {
     u64 p = 1;
@@ -131,7 +149,7 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     I->table = I->aset = I->bset = nullptr;
     const fgk_det* d = (const fgk_det*)dets;
     u64 tsize = pow2_at_least((u64)(n > 0 ? 2 * n : 1) < 64 ? 64 : (u64)2 * n);
-    FGK_CUDA(cudaMalloc((void**)&I->table, tsize * sizeof(u64)));
+    FGK_CUDA(pool_alloc((void**)&I->table, tsize * sizeof(u64), st, device));
     FGK_CUDA(cudaMemsetAsync(I->table, 0xFF, tsize * sizeof(u64), st));
     if (n > 0) {
         k_index_insert<<<grid1d(n, device), 256, 0, st>>>(d, n, I->table, tsize - 1);
@@ -141,9 +159,9 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     // strings, second pass into a right-sized (cache friendly) one
     unsigned long long* d_cnt = nullptr;
     u64* tmp = nullptr;
-    FGK_CUDA(cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)));
+    FGK_CUDA(pool_alloc((void**)&d_cnt, 2 * sizeof(unsigned long long), st, device));
     FGK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
-    FGK_CUDA(cudaMalloc((void**)&tmp, tsize * sizeof(u64)));
+    FGK_CUDA(pool_alloc((void**)&tmp, tsize * sizeof(u64), st, device));
     unsigned long long h_cnt[2] = {0, 0};
     for (int which = 0; which < 2 && n > 0; which++) {
         FGK_CUDA(cudaMemsetAsync(tmp, 0xFF, tsize * sizeof(u64), st));
@@ -156,8 +174,8 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     I->n_beta_strings = (i64)h_cnt[1];
     u64 asz = pow2_at_least(h_cnt[0] * 4 < 64 ? 64 : h_cnt[0] * 4);
     u64 bsz = pow2_at_least(h_cnt[1] * 4 < 64 ? 64 : h_cnt[1] * 4);
-    FGK_CUDA(cudaMalloc((void**)&I->aset, asz * sizeof(u64)));
-    FGK_CUDA(cudaMalloc((void**)&I->bset, bsz * sizeof(u64)));
+    FGK_CUDA(pool_alloc((void**)&I->aset, asz * sizeof(u64), st, device));
+    FGK_CUDA(pool_alloc((void**)&I->bset, bsz * sizeof(u64), st, device));
     FGK_CUDA(cudaMemsetAsync(I->aset, 0xFF, asz * sizeof(u64), st));
     FGK_CUDA(cudaMemsetAsync(I->bset, 0xFF, bsz * sizeof(u64), st));
     if (n > 0) {
@@ -168,8 +186,8 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     }
     // dense lists of the distinct strings (scanned by the projected-H builder)
     I->alist = I->blist = nullptr;
-    FGK_CUDA(cudaMalloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64)));
-    FGK_CUDA(cudaMalloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64)));
+    FGK_CUDA(pool_alloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64), st, device));
+    FGK_CUDA(pool_alloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64), st, device));
     FGK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
     if (n > 0) {
         k_set_compact<<<grid1d((i64)asz, device), 256, 0, st>>>(I->aset, asz, I->alist, d_cnt);
@@ -188,22 +206,22 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
         std::sort(hl.begin(), hl.end());
         FGK_CUDA(cudaMemcpy(dl, hl.data(), m * sizeof(u64), cudaMemcpyHostToDevice));
     }
-    cudaFree(tmp);
-    cudaFree(d_cnt);
+    cudaFreeAsync(tmp, st);
+    cudaFreeAsync(d_cnt, st);
     // rank form: string ranks per determinant and, when the basis covers at least 1/16 of its
     // alpha x beta string product (always for CAS-like / product bases), the dense pair table
     // the rank-based projected-H builder reads instead of probing the hash table
     I->ra = I->rb = I->pair = nullptr;
     if (n > 0) {
-        FGK_CUDA(cudaMalloc((void**)&I->ra, (size_t)n * sizeof(int32_t)));
-        FGK_CUDA(cudaMalloc((void**)&I->rb, (size_t)n * sizeof(int32_t)));
+        FGK_CUDA(pool_alloc((void**)&I->ra, (size_t)n * sizeof(int32_t), st, device));
+        FGK_CUDA(pool_alloc((void**)&I->rb, (size_t)n * sizeof(int32_t), st, device));
         k_string_ranks<<<grid1d(n, device), 256, 0, st>>>(d, n, I->alist, I->n_alpha_strings, I->blist,
                                                           I->n_beta_strings, I->ra, I->rb);
         FGK_LAUNCH_CHECK();
         const i64 prod = I->n_alpha_strings * I->n_beta_strings;
         const i64 lim = 16 * n > (1ll << 20) ? 16 * n : (1ll << 20);
         if (prod <= lim && prod < (1ll << 31)) {
-            FGK_CUDA(cudaMalloc((void**)&I->pair, (size_t)prod * sizeof(int32_t)));
+            FGK_CUDA(pool_alloc((void**)&I->pair, (size_t)prod * sizeof(int32_t), st, device));
             FGK_CUDA(cudaMemsetAsync(I->pair, 0xFF, (size_t)prod * sizeof(int32_t), st));
             k_pair_fill<<<grid1d(n, device), 256, 0, st>>>(I->ra, I->rb, n, I->n_beta_strings, I->pair);
             FGK_LAUNCH_CHECK();
@@ -223,9 +241,12 @@ extern "C" int fgk_index_destroy(fgk_index_t idx)
 {
     if (!idx) return FGK_OK;
     cudaSetDevice(idx->device);
-    cudaFree(idx->table); cudaFree(idx->aset); cudaFree(idx->bset);
-    cudaFree(idx->alist); cudaFree(idx->blist);
-    cudaFree(idx->ra); cudaFree(idx->rb); cudaFree(idx->pair);
+    // same guarantee as cudaFree (no kernel on any stream still reads the tables), but the blocks
+    // go back to the pool instead of the driver
+    cudaDeviceSynchronize();
+    void* bufs[8] = {idx->table, idx->aset, idx->bset, idx->alist, idx->blist, idx->ra, idx->rb, idx->pair};
+    for (void* b : bufs)
+        if (b) cudaFreeAsync(b, 0);
     delete idx;
     return FGK_OK;
 }
