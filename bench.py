@@ -260,8 +260,52 @@ def workload_config(args, l2_note):
             "l2": l2_note}
 
 
+class CleanStdout:
+    """stdout must carry exactly one JSON line, but libraries write there too (NCCL prints its
+    version banner on fd 1 when NCCL_DEBUG is set in the environment).  While active, fd 1 points at
+    stderr; emit() writes to the real stdout."""
+
+    def __init__(self):
+        self.saved = None
+
+    def __enter__(self):
+        try:
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+        except OSError:
+            self.saved = None
+        return self
+
+    def emit(self, text):
+        data = (text.rstrip("\n") + "\n").encode()
+        if self.saved is None:
+            sys.stdout.write(data.decode())
+            sys.stdout.flush()
+            return
+        sys.stdout.flush()
+        while data:
+            data = data[os.write(self.saved, data):]
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                sys.stdout.flush()
+                os.dup2(self.saved, 1)
+                os.close(self.saved)
+            except OSError:
+                pass
+            self.saved = None
+        return False
+
+
 # ---- GPU arm -------------------------------------------------------------------------------------
 def run_ours(args):
+    with CleanStdout() as out:
+        _run_ours(args, out)
+
+
+def _run_ours(args, out):
     import torch
     import torch.distributed as dist
     import flow_guided_krylov_b200 as fgk
@@ -274,9 +318,6 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout carries the one
-        # JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     def barrier():
@@ -624,7 +665,7 @@ def run_ours(args):
                            if fused else "SELL H.v + NCCL all-gather"),
         "build": build, "pt2": pt2, "connections": conn, "krylov": krylov, "packed_f32_storage": packed,
     }
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

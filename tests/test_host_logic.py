@@ -149,3 +149,27 @@ def test_sort_unique_dets_is_reference_order():
     out = sort_unique_dets(d, 64).numpy().view(np.uint64)
     keys = [(int(a) << 64) | int(b) for a, b in out]
     assert keys == sorted(set(keys)) and len(keys) == 4
+
+
+def test_bench_stdout_carries_only_the_json_line(tmp_path):
+    """bench.py's stdout guard: C-level writes to fd 1 (NCCL's version banner) and Python prints
+    inside the run go to stderr; only the emitted JSON line reaches stdout."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "t.py"
+    script.write_text(
+        "import sys, ctypes, json\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from bench import CleanStdout\n"
+        "libc = ctypes.CDLL(None)\n"
+        "with CleanStdout() as out:\n"
+        "    libc.puts(b'NCCL version 2.28.9+cuda12.9'); libc.fflush(None)\n"
+        "    print('chatter')\n"
+        "    out.emit(json.dumps({'metric': 'm', 'value': 1.5}))\n")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout) == {"metric": "m", "value": 1.5}
+    assert "NCCL version" in r.stderr and "chatter" in r.stderr
