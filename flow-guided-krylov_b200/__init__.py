@@ -18,7 +18,8 @@ from .expansion import (Pt2Workspace, ResidualBasedExpander, ResidualExpansionCo
                         SelectedCIExpander, default_pt2_workspace, pt2_candidates, pt2_select, select_top_k)
 from .skqd import FlowGuidedSKQD, SampleBasedKrylovDiagonalization, SKQDConfig  # noqa: F401
 from .solvers import expm_multiply, lowest_eigenpairs  # noqa: F401
-from .sto3g import (compute_molecular_integrals, create_beh2_hamiltonian, create_h2_hamiltonian,  # noqa: F401
-                    create_h2o_hamiltonian, create_lih_hamiltonian, create_n2_hamiltonian)
+from .sto3g import (compute_molecular_integrals, create_beh2_hamiltonian, create_ch4_hamiltonian,  # noqa: F401
+                    create_h2_hamiltonian, create_h2o_hamiltonian, create_lih_hamiltonian,
+                    create_n2_hamiltonian, create_nh3_hamiltonian)
 
 __version__ = "0.1.0"

@@ -342,29 +342,64 @@ def lih_geometry(bond_length=1.6):
     return [("Li", (0.0, 0.0, 0.0)), ("H", (0.0, 0.0, bond_length))]
 
 
-def beh2_geometry(bond_length=1.33):
-    return [("Be", (0.0, 0.0, 0.0)), ("H", (0.0, 0.0, bond_length)), ("H", (0.0, 0.0, -bond_length))]
-
-
-def n2_geometry(bond_length=1.10):
-    return [("N", (0.0, 0.0, 0.0)), ("N", (0.0, 0.0, bond_length))]
-
-
 def h2o_geometry(oh_length=0.96, angle=104.5):
     a = np.radians(angle)
     return [("O", (0.0, 0.0, 0.0)), ("H", (oh_length, 0.0, 0.0)),
             ("H", (oh_length * np.cos(a), oh_length * np.sin(a), 0.0))]
 
 
-def _factory(geom_fn):
-    def make(*args, device="cuda", **kw):
-        from .hamiltonian import MolecularHamiltonian
-        return MolecularHamiltonian(compute_molecular_integrals(geom_fn(*args, **kw)), device=device)
-    return make
+def beh2_geometry(bond_length=1.33):
+    return [("Be", (0.0, 0.0, 0.0)), ("H", (0.0, 0.0, bond_length)), ("H", (0.0, 0.0, -bond_length))]
 
 
-create_h2_hamiltonian = _factory(h2_geometry)
-create_lih_hamiltonian = _factory(lih_geometry)
-create_beh2_hamiltonian = _factory(beh2_geometry)
-create_n2_hamiltonian = _factory(n2_geometry)
-create_h2o_hamiltonian = _factory(h2o_geometry)
+def nh3_geometry(nh_length=1.01, hnh_angle=107.8):
+    ang = np.radians(hnh_angle)
+    h = nh_length * np.cos(np.arcsin(np.sin(ang / 2) / np.sin(np.radians(60))))
+    r = np.sqrt(nh_length ** 2 - h ** 2)
+    return [("N", (0.0, 0.0, h)), ("H", (r, 0.0, 0.0)),
+            ("H", (r * np.cos(np.radians(120)), r * np.sin(np.radians(120)), 0.0)),
+            ("H", (r * np.cos(np.radians(240)), r * np.sin(np.radians(240)), 0.0))]
+
+
+def n2_geometry(bond_length=1.10):
+    return [("N", (0.0, 0.0, 0.0)), ("N", (0.0, 0.0, bond_length))]
+
+
+def ch4_geometry(ch_length=1.09):
+    a = ch_length / np.sqrt(3)
+    return [("C", (0.0, 0.0, 0.0)), ("H", (a, a, a)), ("H", (a, -a, -a)), ("H", (-a, a, -a)),
+            ("H", (-a, -a, a))]
+
+
+def _make(geometry, device):
+    from .hamiltonian import MolecularHamiltonian
+    return MolecularHamiltonian(compute_molecular_integrals(geometry, basis="sto-3g"), device=device)
+
+
+# same names, parameters and defaults as the reference's factories (device: CUDA only here)
+def create_h2_hamiltonian(bond_length: float = 0.74, device: str = "cuda"):
+    return _make(h2_geometry(bond_length), device)
+
+
+def create_lih_hamiltonian(bond_length: float = 1.6, device: str = "cuda"):
+    return _make(lih_geometry(bond_length), device)
+
+
+def create_h2o_hamiltonian(oh_length: float = 0.96, angle: float = 104.5, device: str = "cuda"):
+    return _make(h2o_geometry(oh_length, angle), device)
+
+
+def create_beh2_hamiltonian(bond_length: float = 1.33, device: str = "cuda"):
+    return _make(beh2_geometry(bond_length), device)
+
+
+def create_nh3_hamiltonian(nh_length: float = 1.01, hnh_angle: float = 107.8, device: str = "cuda"):
+    return _make(nh3_geometry(nh_length, hnh_angle), device)
+
+
+def create_n2_hamiltonian(bond_length: float = 1.10, device: str = "cuda"):
+    return _make(n2_geometry(bond_length), device)
+
+
+def create_ch4_hamiltonian(ch_length: float = 1.09, device: str = "cuda"):
+    return _make(ch4_geometry(ch_length), device)

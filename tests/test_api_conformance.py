@@ -72,3 +72,14 @@ def test_skqd_interface(mods):
     mine = {x.name: x.default for x in dataclasses.fields(f.SKQDConfig)}
     for k, v in ref.items():
         assert k in mine and mine[k] == v, f"SKQDConfig.{k}"
+
+
+def test_integral_front_end_interface(mods):
+    """compute_molecular_integrals and the molecule factories keep the reference's names,
+    parameters and default geometries (molecular.py:945-1139)."""
+    rm, _, _, f = mods
+    _assert_superset(rm.compute_molecular_integrals, f.compute_molecular_integrals, "compute_molecular_integrals")
+    for name in ("create_h2_hamiltonian", "create_lih_hamiltonian", "create_h2o_hamiltonian",
+                 "create_beh2_hamiltonian", "create_nh3_hamiltonian", "create_n2_hamiltonian",
+                 "create_ch4_hamiltonian"):
+        _assert_superset(getattr(rm, name), getattr(f, name), name)
