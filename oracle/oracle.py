@@ -258,10 +258,25 @@ class OracleHam:
         else:
             imp = (c64 * c64) / (np.abs(float(energy) - ex) + 1e-10)   # :547-548
         nsel = min(int(k), len(cand))                                  # :551
-        # deterministic order: importance descending, key ascending
-        kord = np.lexsort(tuple(cand[:, ::-1].T) + (-imp,))
-        top = kord[:nsel]
-        return cand[top], imp[top], cand, imp, raw
+        if nsel == 0:
+            return cand[:0], imp[:0], cand, imp, raw
+        # The reference's torch.topk leaves ties unspecified (:552).  Deterministic protocol,
+        # the same as the product's select_top_k: candidates within a relative 1e-9 of the k-th
+        # importance count as tied with it (symmetry-equivalent determinants of a real molecule
+        # are exactly degenerate; their FP64 sums differ in the last bits only through the
+        # summation order) and the tie is broken by ascending key; result ordered by importance
+        # descending, key ascending.
+        kth = np.sort(imp)[::-1][nsel - 1]
+        band = 1e-9 * abs(kth)
+        sure = np.nonzero(imp > kth + band)[0]
+        tie = np.nonzero((imp >= kth - band) & (imp <= kth + band))[0]
+        need = nsel - len(sure)
+        if len(tie) > need:
+            tie = tie[np.lexsort(tuple(cand[tie][:, ::-1].T))[:need]]
+        pick = np.concatenate([sure, tie])
+        pick = pick[np.lexsort(tuple(cand[pick][:, ::-1].T))]          # key ascending ...
+        pick = pick[np.argsort(-imp[pick], kind="stable")]             # ... inside importance descending
+        return cand[pick], imp[pick], cand, imp, raw
 
     # residual_expansion.py:334-406
     def expand_basis(self, basis, k):

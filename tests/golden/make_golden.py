@@ -66,8 +66,28 @@ def synth_arrays(n_orb, seed=0, h1_scale=1.0, h2_scale=0.1, sparsify=0.0):
     return h1.astype(np.float32).astype(np.float64), g.astype(np.float32).astype(np.float64)
 
 
-def make_h(n_orb, na, nb, seed=0, e_nuc=0.0, **kw):
-    h1, g = synth_arrays(n_orb, seed, **kw)
+MOLECULES = {}      # name -> (h1, g, e_nuc): real STO-3G integrals, float32-rounded
+
+
+def molecule_arrays(molecule):
+    """Real STO-3G / RHF integrals of the reference's own molecules (its factories' default
+    geometries, molecular.py:1019-1115) from the repository's PySCF-free front-end."""
+    if molecule not in MOLECULES:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+        from flow_guided_krylov_b200 import sto3g
+        geom = {"lih": sto3g.lih_geometry, "beh2": sto3g.beh2_geometry, "n2": sto3g.n2_geometry}[molecule]()
+        I = sto3g.compute_molecular_integrals(geom)
+        MOLECULES[molecule] = (I.h1e.astype(np.float32).astype(np.float64),
+                               I.h2e.astype(np.float32).astype(np.float64), float(I.nuclear_repulsion))
+    return MOLECULES[molecule]
+
+
+def make_h(n_orb, na, nb, seed=0, e_nuc=0.0, molecule=None, **kw):
+    if molecule is not None:
+        h1, g, e_nuc = molecule_arrays(molecule)
+        assert h1.shape == (n_orb, n_orb)
+    else:
+        h1, g = synth_arrays(n_orb, seed, **kw)
     integ = MolecularIntegrals(h1, g, e_nuc, na + nb, n_orb, na, nb)
     return MolecularHamiltonian(integ, device="cpu"), h1, g
 
@@ -113,6 +133,7 @@ def connections_block(H, dets):
 
 def gen_hamiltonian_case(name, n_orb, na, nb, seed, n_rand, n_basis, e_nuc=0.0, **kw):
     H, h1, g = make_h(n_orb, na, nb, seed, e_nuc=e_nuc, **kw)
+    e_nuc = float(H.nuclear_repulsion) if hasattr(H, "nuclear_repulsion") else e_nuc
     rng = np.random.default_rng(1000 + seed)
     hf = H.get_hf_state().numpy()
     dets = np.concatenate([hf[None], random_dets(n_orb, na, nb, n_rand, rng)])
@@ -133,8 +154,8 @@ def gen_hamiltonian_case(name, n_orb, na, nb, seed, n_rand, n_basis, e_nuc=0.0, 
     return H
 
 
-def gen_expander_case(name, n_orb, na, nb, seed, k, rounds, start="hf"):
-    H, h1, g = make_h(n_orb, na, nb, seed)
+def gen_expander_case(name, n_orb, na, nb, seed, k, rounds, start="hf", molecule=None):
+    H, h1, g = make_h(n_orb, na, nb, seed, molecule=molecule)
     hf = H.get_hf_state()
     if start == "hf":
         b = torch.stack([hf])
@@ -143,7 +164,7 @@ def gen_expander_case(name, n_orb, na, nb, seed, k, rounds, start="hf"):
         b = torch.unique(torch.from_numpy(
             np.concatenate([hf.numpy()[None], random_dets(n_orb, na, nb, start, rng)])), dim=0)
     out = dict(shape=np.array([n_orb, na, nb]), h1=h1.astype(np.float32), g=g.astype(np.float32), k=np.array(k),
-               basis0=b.numpy().astype(np.uint8))
+               basis0=b.numpy().astype(np.uint8), e_nuc=np.array(float(getattr(H, "nuclear_repulsion", 0.0))))
     ex = SelectedCIExpander(H, ResidualExpansionConfig(max_configs_per_iter=k))
     for rd in range(rounds):
         # the inner selection, on the reference's own eigenpair
@@ -231,12 +252,26 @@ def gen_skqd_case(name, n_orb, na, nb, seed, h2_scale, kdim, shots, n_nf):
           f"best {res['best_stable_energy']:.9f}")
 
 
-def gen_fci(name, n_orb, na, nb, seed):
-    H, h1, g = make_h(n_orb, na, nb, seed)
+def gen_fci(name, n_orb, na, nb, seed, molecule=None):
+    H, h1, g = make_h(n_orb, na, nb, seed, molecule=molecule)
     e = quiet(H.fci_energy)
     np.savez_compressed(os.path.join(OUT, f"fci_{name}.npz"),
-                        shape=np.array([n_orb, na, nb]), h1=h1.astype(np.float32), g=g.astype(np.float32), fci=np.array(e))
+                        shape=np.array([n_orb, na, nb]), h1=h1.astype(np.float32), g=g.astype(np.float32), fci=np.array(e),
+                        e_nuc=np.array(float(getattr(H, "nuclear_repulsion", 0.0))))
     print(f"fci_{name}: {e:.10f}")
+
+
+def main_molecules():
+    """fixtures on REAL STO-3G integrals (symmetry zeros, numerical-noise entries around the
+    1e-12 filters, non-zero nuclear repulsion); kept separate so that the synthetic fixtures
+    of the first generation stay byte-identical"""
+    torch.set_num_threads(1)
+    gen_hamiltonian_case("lih_sto3g", 6, 2, 2, 0, n_rand=24, n_basis=60, molecule="lih")
+    gen_hamiltonian_case("beh2_sto3g", 7, 3, 3, 0, n_rand=16, n_basis=80, molecule="beh2")
+    gen_hamiltonian_case("n2_sto3g", 10, 7, 7, 0, n_rand=6, n_basis=120, molecule="n2")
+    gen_fci("lih_sto3g", 6, 2, 2, 0, molecule="lih")
+    gen_expander_case("lih_sto3g", 6, 2, 2, 0, k=10, rounds=3, molecule="lih")
+    gen_expander_case("beh2_sto3g", 7, 3, 3, 0, k=20, rounds=3, molecule="beh2")
 
 
 def main():
@@ -261,4 +296,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--molecules" in sys.argv:
+        main_molecules()
+    else:
+        main()

@@ -9,7 +9,8 @@ from oracle import oracle as orc
 from conftest import load_golden
 from helpers import hostcheck, pack_np, unpack_np
 
-CASES = ["lih", "beh2", "n2", "ragged", "sparse", "edge_full_alpha", "edge_no_beta", "wide"]
+CASES = ["lih", "beh2", "n2", "ragged", "sparse", "edge_full_alpha", "edge_no_beta", "wide",
+         "lih_sto3g", "beh2_sto3g", "n2_sto3g"]
 
 
 def _p(a):
