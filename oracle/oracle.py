@@ -88,6 +88,22 @@ def keys_of(cfgs):
     return out
 
 
+def top_k_protocol(cand, imp, nsel):
+    """indices of the nsel selected candidates: everything clearly above the nsel-th importance,
+    then the members of its relative-1e-9 tie band by ascending key; ordered by importance
+    descending, key ascending (cand: (m, S) 0/1 rows, site 0 most significant)."""
+    kth = np.sort(imp)[::-1][nsel - 1]
+    band = 1e-9 * abs(kth)
+    sure = np.nonzero(imp > kth + band)[0]
+    tie = np.nonzero((imp >= kth - band) & (imp <= kth + band))[0]
+    need = nsel - len(sure)
+    if len(tie) > need:
+        tie = tie[np.lexsort(tuple(cand[tie][:, ::-1].T))[:need]]
+    pick = np.concatenate([sure, tie])
+    pick = pick[np.lexsort(tuple(cand[pick][:, ::-1].T))]          # key ascending ...
+    return pick[np.argsort(-imp[pick], kind="stable")]             # ... inside importance descending
+
+
 class OracleHam:
     """MolecularHamiltonian (molecular.py:35-117) over float32 tables."""
 
@@ -266,16 +282,7 @@ class OracleHam:
         # are exactly degenerate; their FP64 sums differ in the last bits only through the
         # summation order) and the tie is broken by ascending key; result ordered by importance
         # descending, key ascending.
-        kth = np.sort(imp)[::-1][nsel - 1]
-        band = 1e-9 * abs(kth)
-        sure = np.nonzero(imp > kth + band)[0]
-        tie = np.nonzero((imp >= kth - band) & (imp <= kth + band))[0]
-        need = nsel - len(sure)
-        if len(tie) > need:
-            tie = tie[np.lexsort(tuple(cand[tie][:, ::-1].T))[:need]]
-        pick = np.concatenate([sure, tie])
-        pick = pick[np.lexsort(tuple(cand[pick][:, ::-1].T))]          # key ascending ...
-        pick = pick[np.argsort(-imp[pick], kind="stable")]             # ... inside importance descending
+        pick = top_k_protocol(cand, imp, nsel)
         return cand[pick], imp[pick], cand, imp, raw
 
     # residual_expansion.py:334-406

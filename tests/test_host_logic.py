@@ -173,3 +173,31 @@ def test_bench_stdout_carries_only_the_json_line(tmp_path):
     assert r.returncode == 0, r.stderr
     assert json.loads(r.stdout) == {"metric": "m", "value": 1.5}
     assert "NCCL version" in r.stderr and "chatter" in r.stderr
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_select_top_k_equals_the_oracle_tie_protocol(seed):
+    """The product's select_top_k (torch, runs on CPU tensors too) and the oracle's top_k_protocol
+    pick the same candidates when groups of exactly / nearly degenerate scores straddle the cut --
+    the situation real molecules create (symmetry-equivalent determinants), where the two sides see
+    last-bit different sums."""
+    import torch
+    from flow_guided_krylov_b200.expansion import select_top_k
+    from helpers import pack_np, random_dets
+    from oracle import oracle as orc
+    rng = np.random.default_rng(seed)
+    n_orb = [6, 20, 33, 48, 64, 10][seed]
+    cfg = np.unique(random_dets(n_orb, 3, 2, 400, rng), axis=0)
+    m = len(cfg)
+    base = rng.random(m // 4 + 1) ** 4                       # few distinct levels -> big tie groups
+    score = base[rng.integers(0, len(base), m)]
+    noise_a = score * (1.0 + 1e-15 * rng.standard_normal(m))   # what "the GPU" sees
+    noise_b = score * (1.0 + 1e-15 * rng.standard_normal(m))   # what "the oracle" sees
+    dets = torch.from_numpy(pack_np(cfg, n_orb).view(np.int64))
+    for k in (1, 5, m // 3, m // 2, m - 1, m, m + 7):
+        sd, ss = select_top_k(dets, torch.from_numpy(noise_a), k, n_orb)
+        pick = orc.top_k_protocol(cfg, noise_b, min(k, m))
+        mine = {bytes(r) for r in sd.numpy().view(np.uint64)}
+        theirs = {bytes(r) for r in pack_np(cfg[pick], n_orb)}
+        assert mine == theirs and len(mine) == min(k, m)
+        assert np.all(np.diff(ss.numpy()) <= 1e-9 * ss.numpy()[:-1])
