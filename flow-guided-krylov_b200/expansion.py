@@ -90,6 +90,7 @@ class Pt2Workspace:
         nat.check(nat.lib().fgk_pt2_reset(self._h, nat.stream_ptr(self.device)))
 
     def accumulate(self, ham, index, src_idx, coeff, mode=nat.PT2_SUM, n_pass=1, pass_id=0):
+        ham._require_particle_numbers(index, "PT2 accumulate")
         src_idx = src_idx.to(torch.int64).contiguous()
         coeff = coeff.to(torch.float64).contiguous()
         nat.check(nat.lib().fgk_pt2_accumulate(

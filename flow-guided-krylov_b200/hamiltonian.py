@@ -288,6 +288,15 @@ class BasisIndex:
                     dense_pairs=bool(dense.value))
 
 
+def popcount64(x: torch.Tensor) -> torch.Tensor:
+    """number of set bits of every int64 element (SWAR; works on CPU and CUDA tensors)."""
+    m1, m2, m4 = 0x5555555555555555, 0x3333333333333333, 0x0F0F0F0F0F0F0F0F
+    x = x - ((x >> 1) & m1)
+    x = (x & m2) + ((x >> 2) & m2)
+    x = (x + (x >> 4)) & m4
+    return ((x * 0x0101010101010101) >> 56) & 0xFF
+
+
 def sort_unique_dets(dets, n_orb):
     """Sorted set of packed determinants: ascending (alpha, beta) as unsigned
     128-bit == the row order of torch.unique(configs, dim=0)
@@ -473,6 +482,23 @@ class MolecularHamiltonian:
         res = out + off
         return res.real if res.is_complex() else res
 
+    def _require_particle_numbers(self, index: "BasisIndex", what: str):
+        """The row builders and the PT2 walk size their per-warp excitation lists from this
+        Hamiltonian's n_alpha / n_beta: every determinant of an indexed basis must carry exactly
+        those particle numbers (the pipeline's bases always do).  get_connections,
+        diagonal_elements_batch and matrix_elements accept any occupation, like the reference.
+        Checked once per index."""
+        key = (self.n_alpha, self.n_beta)
+        if getattr(index, "_particles_ok", None) == key or len(index) == 0:
+            return
+        cnt = popcount64(index.dets)
+        bad = (cnt[:, 0] != self.n_alpha) | (cnt[:, 1] != self.n_beta)
+        if bool(bad.any()):
+            i = int(torch.nonzero(bad)[0])
+            raise ValueError(f"{what}: determinant {i} of the basis has {int(cnt[i, 0])}+{int(cnt[i, 1])} "
+                             f"electrons, the Hamiltonian has {self.n_alpha}+{self.n_beta}")
+        index._particles_ok = key
+
     # ---- projected Hamiltonian (K4 + K5) ---------------------------------------------------
     def projected_csr(self, basis, mode=nat.H_RAW, row_begin=0, row_end=None, sort_rows=False,
                       index: Optional[BasisIndex] = None, packed=False, profile=False) -> ProjectedH:
@@ -482,6 +508,7 @@ class MolecularHamiltonian:
         care.  sort_rows=True / .sort_rows() / .to_scipy() order them by column."""
         dets = basis if packed else self.pack(basis)
         idx = index if index is not None else BasisIndex(dets)
+        self._require_particle_numbers(idx, "projected_csr")
         n = len(idx)
         row_end = n if row_end is None else row_end
         rows = row_end - row_begin
@@ -528,6 +555,7 @@ class MolecularHamiltonian:
         views (to_dense, to_scipy, sort_rows) are not available on it."""
         dets = basis if packed else self.pack(basis)
         idx = index if index is not None else BasisIndex(dets)
+        self._require_particle_numbers(idx, "projected_sell")
         n = len(idx)
         row_end = n if row_end is None else row_end
         rows = row_end - row_begin

@@ -235,7 +235,9 @@ class SampleBasedKrylovDiagonalization:
             k = min(self.config.num_eigenvalues, n - 1)
             w, v = lowest_eigenpairs(P, k=k)
             w = w + reg
-        if n < 100 or return_eigenvector or not self.config.reference_compat:               # :754-758,:790-793
+        # the unchanged pipeline passes the REFERENCE's SKQDConfig, which has no such field
+        compat = getattr(self.config, "reference_compat", True)
+        if n < 100 or return_eigenvector or not compat:                                     # :754-758,:790-793
             E0 = float(w[0])
         else:                                                                               # :794-796, SURVEY F5
             E0 = float(w[min(self.config.num_eigenvalues, n - 1) - 1])

@@ -83,3 +83,38 @@ def test_integral_front_end_interface(mods):
                  "create_beh2_hamiltonian", "create_nh3_hamiltonian", "create_n2_hamiltonian",
                  "create_ch4_hamiltonian"):
         _assert_superset(getattr(rm, name), getattr(f, name), name)
+
+
+def test_mirror_classes_accept_the_reference_config_objects(mods):
+    """pipeline.py hands its OWN ResidualExpansionConfig / SKQDConfig instances to the classes it
+    instantiates (pipeline.py:505-515, :700-712): every `self.config.<field>` our mirrors read
+    must exist on the reference's dataclasses."""
+    import re
+    _, rx, rs, f = mods
+    import flow_guided_krylov_b200.expansion as fexp
+    root = os.path.dirname(os.path.abspath(fexp.__file__))
+    for fname, ref_cfg in (("expansion.py", rx.ResidualExpansionConfig()), ("skqd.py", rs.SKQDConfig())):
+        src = open(os.path.join(root, fname)).read()
+        for attr in set(re.findall(r"self\.config\.(\w+)", src)):
+            assert hasattr(ref_cfg, attr), f"{fname}: self.config.{attr} is not a field of the reference config"
+
+
+def test_integration_recipe_of_INTEGRATION_md(mods):
+    """The no-edit integration of INTEGRATION.md section 3, as far as it goes without a GPU: the
+    combined class is constructible (MRO) and passes pipeline.py:318's isinstance check at class
+    level; the names the recipe patches exist where pipeline.py looks them up."""
+    rm, rx, rs, f = mods
+
+    class MolecularHamiltonian(f.MolecularHamiltonian, rm.MolecularHamiltonian):
+        def __init__(self, integrals, device="cuda"):
+            f.MolecularHamiltonian.__init__(self, integrals, device)
+
+    assert issubclass(MolecularHamiltonian, rm.MolecularHamiltonian)
+    # our methods win over the reference's in the MRO
+    for m in ("get_connections", "diagonal_elements_batch", "matrix_elements_fast", "fci_energy", "get_hf_state"):
+        assert getattr(MolecularHamiltonian, m) is getattr(f.MolecularHamiltonian, m)
+    assert hasattr(rx, "SelectedCIExpander") and hasattr(rx, "ResidualBasedExpander") and hasattr(rs, "FlowGuidedSKQD")
+    src = open(os.path.join(REF, "pipeline.py")).read()
+    assert "from krylov.residual_expansion import SelectedCIExpander" in src      # late import: patch the module
+    assert "isinstance(hamiltonian, MolecularHamiltonian)" in src
+    assert "skqd = FlowGuidedSKQD(" in src                                         # module-level name: patch pipeline.FlowGuidedSKQD

@@ -201,3 +201,36 @@ def test_select_top_k_equals_the_oracle_tie_protocol(seed):
         theirs = {bytes(r) for r in pack_np(cfg[pick], n_orb)}
         assert mine == theirs and len(mine) == min(k, m)
         assert np.all(np.diff(ss.numpy()) <= 1e-9 * ss.numpy()[:-1])
+
+
+def test_particle_number_guard_of_indexed_bases():
+    """projected_csr / projected_sell / PT2 accumulate size per-warp lists from the Hamiltonian's
+    n_alpha / n_beta; a basis with other particle numbers must be refused up front (host check,
+    runs on CPU tensors)."""
+    import types
+    import torch
+    from flow_guided_krylov_b200.hamiltonian import MolecularHamiltonian, popcount64
+    from helpers import pack_np, random_dets
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 2 ** 64, size=5000, dtype=np.uint64)
+    x[:4] = [0, 2 ** 64 - 1, 2 ** 63, 1]
+    assert np.array_equal(popcount64(torch.from_numpy(x.view(np.int64))).numpy(),
+                          [bin(int(v)).count("1") for v in x])
+    ham = types.SimpleNamespace(n_alpha=3, n_beta=2)
+
+    class Idx:
+        def __init__(self, dets):
+            self.dets = dets
+
+        def __len__(self):
+            return self.dets.shape[0]
+
+    good = torch.from_numpy(pack_np(random_dets(20, 3, 2, 50, rng), 20).view(np.int64))
+    idx = Idx(good)
+    MolecularHamiltonian._require_particle_numbers(ham, idx, "test")
+    assert idx._particles_ok == (3, 2)
+    bad = good.clone()
+    bad[17, 1] |= 1 << 19                       # one more beta electron (orbital 0 of 20)
+    with pytest.raises(ValueError, match="determinant 17"):
+        MolecularHamiltonian._require_particle_numbers(ham, Idx(bad), "test")
+    MolecularHamiltonian._require_particle_numbers(ham, Idx(good[:0]), "test")      # empty basis: fine
