@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Generate golden vectors by running the REFERENCE itself (CPU, this container).
 
-    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+    python tests/golden/make_golden.py               # synthetic integrals -> tests/golden/*.npz
+    python tests/golden/make_golden.py --molecules   # real LiH / BeH2 / N2 STO-3G integrals
+                                                     # (flow_guided_krylov_b200.sto3g) -> *_sto3g.npz
 
 The reference (/root/reference, pure Python) is imported, never copied.  It
 cannot travel to the GPU box, so its outputs on seeded synthetic integrals
