@@ -7,7 +7,7 @@
  * method (file:line under reference/src) whose work it takes over.  The
  * reference-side binding (ctypes, because the reference host language is
  * Python) is shown in INTEGRATION.md and implemented in
- * flow-guided-krylov_b200/_native.py.
+ * flow_guided_krylov_b200/_native.py.
  *
  * Rules of the boundary
  *   - plain C: pointers, sizes, ints.  No torch/C++ types.

@@ -2,7 +2,7 @@
 of the reference's host-side numerics.  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
-reference legs may import this module.  Nothing under flow-guided-krylov_b200/
+reference legs may import this module.  Nothing under flow_guided_krylov_b200/
 does: the product path fails loudly when its CUDA library is missing.
 
 Parity pin: checked against tests/golden/*.npz, which were produced by running

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "flow-guided-krylov_b200", "csrc")
+CSRC = os.path.join(ROOT, "flow_guided_krylov_b200", "csrc")
 
 
 def pack_np(cfgs, n_orb):

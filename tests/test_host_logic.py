@@ -55,7 +55,7 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "flow-guided-krylov_b200")
+    pkg = os.path.join(ROOT, "flow_guided_krylov_b200")
     for dirpath, _, files in os.walk(pkg):
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
