@@ -98,6 +98,7 @@ class ProjectedH:
             self._diag_cache = self.diagonal().clone()
             self.cols = self.cols[:0]
             self.vals = self.vals[:0]
+            self.sell_only = True
         return self
 
     def to_sell_packed(self, keep_csr=True):
@@ -200,7 +201,7 @@ class ProjectedH:
         reused between calls unless `out` is given).  The call returns when y is complete."""
         if not torch.is_tensor(x_host):
             x_host = torch.from_numpy(np.ascontiguousarray(x_host))
-        dev = self.cols.device if self.cols.numel() else self._sell[1].device
+        dev = self.row_ptr.device
         key = (x_host.dtype, x_host.shape[0])
         buf = getattr(self, "_host_io", None)
         if buf is None or buf[0] != key:

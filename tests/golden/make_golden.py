@@ -4,6 +4,8 @@
     python tests/golden/make_golden.py               # synthetic integrals -> tests/golden/*.npz
     python tests/golden/make_golden.py --molecules   # real LiH / BeH2 / N2 STO-3G integrals
                                                      # (flow_guided_krylov_b200.sto3g) -> *_sto3g.npz
+    python tests/golden/make_golden.py --molecules2 [sci_n2] [skqd_beh2] [skqd_n2]
+                                                     # Stage 3 on N2, Stage 4 on BeH2 / N2 (minutes)
 
 The reference (/root/reference, pure Python) is imported, never copied.  It
 cannot travel to the GPU box, so its outputs on seeded synthetic integrals
@@ -200,8 +202,14 @@ def gen_residual_case(name, n_orb, na, nb, seed, k, iters):
     print(f"res_{name}: size {len(b)} E {st['final_energy']:.9f}")
 
 
-def gen_skqd_case(name, n_orb, na, nb, seed, h2_scale, kdim, shots, n_nf):
-    H, h1, g = make_h(n_orb, na, nb, seed, h2_scale=h2_scale)
+def gen_skqd_case(name, n_orb, na, nb, seed, h2_scale, kdim, shots, n_nf, molecule=None, hashed=False):
+    """hashed=True (large subspaces): the subspace CSR is stored as indptr + SHA-256 digests of
+    the column ids and of the float32 off-diagonal values (the arrays themselves would be tens
+    of MB), the diagonal as the reference's float32 values."""
+    if molecule is not None:
+        H, h1, g = make_h(n_orb, na, nb, seed, molecule=molecule)
+    else:
+        H, h1, g = make_h(n_orb, na, nb, seed, h2_scale=h2_scale)
     rng = np.random.default_rng(5)
     hf = H.get_hf_state().numpy()
     nf = torch.unique(torch.from_numpy(
@@ -228,8 +236,8 @@ def gen_skqd_case(name, n_orb, na, nb, seed, h2_scale, kdim, shots, n_nf):
     out = dict(shape=np.array([n_orb, na, nb]), h1=h1.astype(np.float32), g=g.astype(np.float32), kdim=np.array(kdim),
                shots=np.array(shots), nf_basis=nf.numpy().astype(np.uint8),
                subspace=sub, H_indptr=Hs.indptr.astype(np.int64),
-               H_indices=Hs.indices.astype(np.int32), H_data=Hs.data.real.astype(np.float64),
                H_imag_max=np.array(np.abs(Hs.data.imag).max()),
+               e_nuc=np.array(float(getattr(H, "nuclear_repulsion", 0.0))),
                psi_steps=np.stack(psis), hf_index=np.array(hf_idx),
                energy_nf_only=np.array(res["energy_nf_only"]),
                energies_krylov=np.array(res["energies_krylov"]),
@@ -237,6 +245,18 @@ def gen_skqd_case(name, n_orb, na, nb, seed, h2_scale, kdim, shots, n_nf):
                basis_sizes_krylov=np.array(res["basis_sizes_krylov"]),
                basis_sizes_combined=np.array(res["basis_sizes_combined"]),
                best_stable_energy=np.array(res["best_stable_energy"]))
+    if hashed:
+        import hashlib
+        rows = np.repeat(np.arange(len(sub)), np.diff(Hs.indptr))
+        offd = Hs.indices != rows
+        out["H_indices_sha256"] = np.array(hashlib.sha256(Hs.indices.astype(np.int32).tobytes()).hexdigest())
+        out["H_offdiag_f32_sha256"] = np.array(
+            hashlib.sha256(Hs.data.real[offd].astype(np.float32).tobytes()).hexdigest())
+        out["H_diag32"] = Hs.data.real[~offd].astype(np.float32)
+        out["H_nnz"] = np.array(Hs.nnz)
+    else:
+        out["H_indices"] = Hs.indices.astype(np.int32)
+        out["H_data"] = Hs.data.real.astype(np.float64)
     for k in range(kdim):
         out[f"krylov_basis_{k}"] = sk.get_basis_states(k).numpy().astype(np.uint8)
     # ground-state solver quirks (F5): both return modes on a >=100 and a <100 basis
@@ -276,6 +296,20 @@ def main_molecules():
     gen_expander_case("beh2_sto3g", 7, 3, 3, 0, k=20, rounds=3, molecule="beh2")
 
 
+def main_molecules2():
+    """round-2 fixtures: Stage 3 on N2 and Stage 4 (SKQD) on BeH2 / N2, real STO-3G integrals
+    (residual_expansion.py:334-406, skqd.py:946-1059)"""
+    torch.set_num_threads(1)
+    which = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if not which or "sci_n2" in which:
+        gen_expander_case("n2_sto3g", 10, 7, 7, 0, k=100, rounds=2, start=250, molecule="n2")
+    if not which or "skqd_beh2" in which:
+        gen_skqd_case("beh2_sto3g", 7, 3, 3, 0, h2_scale=None, kdim=4, shots=5000, n_nf=100, molecule="beh2")
+    if not which or "skqd_n2" in which:
+        gen_skqd_case("n2_sto3g", 10, 7, 7, 0, h2_scale=None, kdim=3, shots=3000, n_nf=150, molecule="n2",
+                      hashed=True)
+
+
 def main():
     torch.set_num_threads(1)
     # SURVEY Appendix B shapes + ragged / sparse / edge shapes
@@ -298,7 +332,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if "--molecules" in sys.argv:
+    if "--molecules2" in sys.argv:
+        main_molecules2()
+    elif "--molecules" in sys.argv:
         main_molecules()
     else:
         main()

@@ -376,7 +376,7 @@ def test_skqd_subspace_and_time_evolution(fgk, name):
 def test_skqd_ground_state_energy_modes(fgk):
     g = load_golden("skqd_lih")
     H, O, _ = make_pair(fgk, g)
-    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(max_krylov_dim=2))
+    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(max_krylov_dim=2, reference_compat=True))
     for tag in ("big", "small"):
         b = g[f"gse_{tag}_basis"]
         e_vec, v = sk.compute_ground_state_energy(t64(b), True, 1e-8)
@@ -398,7 +398,7 @@ def test_skqd_run_with_nf_on_reference_samples(fgk):
     H, O, _ = make_pair(fgk, g)
     kdim = int(g["kdim"])
     sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(
-        max_krylov_dim=kdim, shots_per_krylov=int(g["shots"])))
+        max_krylov_dim=kdim, shots_per_krylov=int(g["shots"]), reference_compat=True))   # F5 bug-compat: goldens only
     # feed the reference's own cumulative sample sets (SURVEY 8d parity protocol)
     prev = np.zeros((0, H.num_sites), np.uint8)
     steps = []

@@ -87,7 +87,7 @@ def test_fci_energy(name):
     assert abs(E - float(g["fci"])) < 5e-6          # float32 diagonal envelope
 
 
-@pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide", "lih_sto3g", "beh2_sto3g"])
+@pytest.mark.parametrize("name", ["lih", "beh2", "beh2_wide", "lih_sto3g", "beh2_sto3g", "n2_sto3g"])
 def test_selected_ci_rounds(name):
     g = load_golden("sci_" + name)
     H = ham_of(g)
@@ -113,7 +113,8 @@ def test_selected_ci_rounds(name):
         new_basis, st = H.expand_basis(basis, k)
         ref_basis = g[f"r{rd}_basis"]
         if np.array_equal(new_basis, ref_basis):
-            assert abs(st["final_energy"] - float(g[f"r{rd}_final_energy"])) < 5e-6
+            # float32 diagonals in the reference: the envelope scales with |E| (N2: ~108 Ha)
+            assert abs(st["final_energy"] - float(g[f"r{rd}_final_energy"])) < 5e-6 * max(1.0, abs(st["final_energy"]) / 8.0)
         else:
             # real molecules: symmetry-equivalent determinants have exactly degenerate importances;
             # when such a group straddles the cut the reference's float32 topk picks by rounding
@@ -127,19 +128,41 @@ def test_selected_ci_rounds(name):
         basis = ref_basis                      # next round starts from the reference's basis
 
 
+def check_hashed_csr(M, g):
+    """large subspaces (make_golden.py hashed=True): indptr + SHA-256 of the column ids and of the
+    float32 off-diagonal values + the reference's float32 diagonal"""
+    import hashlib
+    assert np.array_equal(M.indptr, g["H_indptr"]) and M.nnz == int(g["H_nnz"])
+    assert hashlib.sha256(M.indices.astype(np.int32).tobytes()).hexdigest() == str(g["H_indices_sha256"])
+    isdiag = M.indices == np.repeat(np.arange(M.shape[0]), np.diff(M.indptr))
+    assert hashlib.sha256(M.data[~isdiag].astype(np.float32).tobytes()).hexdigest() == str(g["H_offdiag_f32_sha256"])
+    assert np.array_equal(M.data[~isdiag].astype(np.float32).astype(np.float64), M.data[~isdiag])
+    d = M.data[isdiag]
+    assert np.abs(d - g["H_diag32"]).max() < 2e-5 * max(1.0, np.abs(d).max())
+
+
 def test_skqd_subspace_csr_and_time_evolution():
-    for name in ("lih", "h5"):
+    for name in ("lih", "h5", "beh2_sto3g", "n2_sto3g"):
         g = load_golden("skqd_" + name)
         H = ham_of(g)
         sub = H.fci_basis()
         assert np.array_equal(sub, g["subspace"])
         M = H.raw_csr(sub)
+        if "H_indices" not in g:            # hashed fixture: the oracle's matrix carries the evolution
+            M.sort_indices()
+            check_hashed_csr(M, g)
+            psi = np.zeros(len(sub), np.complex128)
+            psi[int(g["hf_index"])] = 1.0
+            for step in range(3):
+                psi = orc.expm_multiply_taylor(M.indptr.astype(np.int64), M.indices, M.data, psi, 0.1)
+                assert np.abs(psi - g["psi_steps"][step]).max() < 2e-5     # float32 diagonal in the reference
+            continue
         assert np.array_equal(M.indptr, g["H_indptr"])
         assert np.array_equal(M.indices, g["H_indices"])
         ref = g["H_data"]
         isdiag = M.indices == np.repeat(np.arange(len(sub)), np.diff(M.indptr))
         assert np.array_equal(M.data[~isdiag], ref[~isdiag])
-        assert np.abs(M.data[isdiag] - ref[isdiag]).max() < 2e-5
+        assert np.abs(M.data[isdiag] - ref[isdiag]).max() < 2e-5 * max(1.0, np.abs(ref).max())
         # time evolution on the REFERENCE's matrix: Taylor vs scipy expm_multiply
         psi = np.zeros(len(sub), np.complex128)
         psi[int(g["hf_index"])] = 1.0
@@ -148,26 +171,35 @@ def test_skqd_subspace_csr_and_time_evolution():
             assert np.abs(psi - g["psi_steps"][step]).max() < 1e-12
 
 
-def test_ground_state_energy_quirk_F5():
-    g = load_golden("skqd_lih")
+@pytest.mark.parametrize("name", ["lih", "beh2_sto3g", "n2_sto3g"])
+def test_ground_state_energy_quirk_F5(name):
+    g = load_golden("skqd_" + name)
     H = ham_of(g)
     for tag in ("big", "small"):
         b = g[f"gse_{tag}_basis"]
         e_vec, v = H.ground_state_energy(b, True)
         e_no, _ = H.ground_state_energy(b, False)
-        assert abs(e_vec - float(g[f"gse_{tag}_E_vec"])) < 5e-6
-        assert abs(e_no - float(g[f"gse_{tag}_E_novec"])) < 5e-6
-        ov = abs(np.dot(v, g[f"gse_{tag}_v"]))
-        assert ov > 1 - 1e-6
+        env = 5e-6 * max(1.0, abs(e_vec) / 8.0)          # float32 diagonals: relative envelope
+        assert abs(e_vec - float(g[f"gse_{tag}_E_vec"])) < env
+        assert abs(e_no - float(g[f"gse_{tag}_E_novec"])) < env
+        # the reference's eigenvector is a ground vector of the oracle's matrix (Rayleigh quotient;
+        # an overlap test would fail on the symmetry-degenerate N2 ground level)
+        D = H.dense_H(b)
+        S = 0.5 * (D + D.T)
+        vr = g[f"gse_{tag}_v"].astype(np.float64)
+        assert abs(vr @ S @ vr / (vr @ vr) + 1e-8 - e_vec) < env
+        assert abs(v @ S @ v + 1e-8 - e_vec) < 1e-9
     assert float(g["gse_big_E_novec"]) > float(g["gse_big_E_vec"]) + 1e-3   # lambda_1, not lambda_0
 
 
-def test_skqd_energies_on_reference_samples():
-    g = load_golden("skqd_lih")
+@pytest.mark.parametrize("name", ["lih", "beh2_sto3g", "n2_sto3g"])
+def test_skqd_energies_on_reference_samples(name):
+    g = load_golden("skqd_" + name)
     H = ham_of(g)
     nf = g["nf_basis"]
     e_nf, _ = H.ground_state_energy(nf, False)
-    assert abs(e_nf - float(g["energy_nf_only"])) < 5e-6
+    env = 5e-6 * max(1.0, abs(e_nf) / 8.0)
+    assert abs(e_nf - float(g["energy_nf_only"])) < env
     for k in range(1, int(g["kdim"])):
         kb = g[f"krylov_basis_{k}"]
         comb = orc.sort_unique(np.concatenate([nf, kb]))
@@ -175,8 +207,8 @@ def test_skqd_energies_on_reference_samples():
         assert len(comb) == int(g["basis_sizes_combined"][k - 1])
         e_k, _ = H.ground_state_energy(kb, False)
         e_c, _ = H.ground_state_energy(comb, False)
-        assert abs(e_k - float(g["energies_krylov"][k - 1])) < 5e-6
-        assert abs(e_c - float(g["energies_combined"][k - 1])) < 5e-6
+        assert abs(e_k - float(g["energies_krylov"][k - 1])) < env
+        assert abs(e_c - float(g["energies_combined"][k - 1])) < env
 
 
 def test_spmv_oracle_vs_numpy():
