@@ -202,6 +202,58 @@ def cpu_sample_csr(args, n_rows_sample, seed=0, tile_to_nnz=0):
     return indptr, indices, data, n, build_s, orc.lib().orc_num_threads(), raw, int(len(cols) + m)
 
 
+def host_threads():
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: the
+    CPU arm sets its own thread count instead of inheriting that)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def set_cpu_threads():
+    from oracle import oracle as orc
+    t = host_threads()
+    orc.lib().orc_set_num_threads(t)
+    return orc.lib().orc_num_threads()
+
+
+def scipy_csr(indptr, indices, data, n):
+    """the matrix in the form the reference holds it (scipy CSR; skqd.py:416, :783)"""
+    import scipy.sparse as sp
+    return sp.csr_matrix((data, indices, indptr), shape=(len(indptr) - 1, n))
+
+
+def reference_connections_rate(args, n_dets=6):
+    """the UNMODIFIED reference's get_connections (molecular.py:194-327) on a few determinants of the
+    same basis, when the reference is vendored under oracle/_ref (tools/vendor_ref.sh)"""
+    src = os.path.join(ROOT, "oracle", "_ref", "src")
+    if not os.path.isdir(src):
+        return None
+    try:
+        import torch
+        for pth in (src, os.path.join(ROOT, "tests", "stubs")):
+            if pth not in sys.path:
+                sys.path.insert(0, pth)
+        import hamiltonians.molecular as ref_mol
+        h1, g = synth_integrals(args.n_orb, seed=0)
+        Hr = ref_mol.MolecularHamiltonian(ref_mol.MolecularIntegrals(
+            h1, g, 0.0, args.n_alpha + args.n_beta, args.n_orb, args.n_alpha, args.n_beta), device="cpu")
+        dets = cas_window_basis(args.n_orb, args.n_frozen, args.n_active, args.n_act_el)
+        pick = np.random.default_rng(3).choice(len(dets), size=n_dets, replace=False)
+        cfg = torch.from_numpy(unpack_np(dets[pick], args.n_orb).astype(np.int64))
+        Hr.get_connections(cfg[0])
+        t0, tot = time.perf_counter(), 0
+        for i in range(n_dets):
+            c, _ = Hr.get_connections(cfg[i])
+            tot += len(c)
+        dt = time.perf_counter() - t0
+        return {"connections_per_s": tot / dt, "dets": n_dets, "seconds": dt,
+                "what": "reference MolecularHamiltonian.get_connections (molecular.py:194-327), device='cpu'"}
+    except Exception as e:          # the baseline leg must never sink the bench line
+        return {"error": str(e)[:200]}
+
+
 def cpu_spmv_rate(indptr, indices, data, n, min_seconds):
     from oracle import oracle as orc
     x = np.random.default_rng(1).standard_normal(n)
@@ -217,47 +269,71 @@ def cpu_spmv_rate(indptr, indices, data, n, min_seconds):
 
 
 def run_reference(args):
+    """CPU arm.  Headline `value`: the C/OpenMP port of the reference's H.v loop (oracle/, scipy's
+    csr_matvec restated) on ALL host cores -- the strongest CPU form of the path, so the GPU/CPU
+    ratio is conservative.  Beside it (cpu_baseline.reference_scipy): the reference's stock code
+    path itself, scipy's single-threaded csr_matvec (what its eigsh / expm_multiply call,
+    skqd.py:291-293,784; residual_expansion.py:435), on the same matrix; and, when the reference is
+    vendored under oracle/_ref, its own get_connections."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    indptr, indices, data, n, build_s, cores, raw, built_nnz = cpu_sample_csr(
+    from oracle import oracle as orc
+    cores = set_cpu_threads()
+    indptr, indices, data, n, build_s, _, raw, built_nnz = cpu_sample_csr(
         args, args.cpu_sample_rows, tile_to_nnz=int(args.cpu_step_nnz))
     nnz = len(data)
     x = np.random.default_rng(1).standard_normal(n)
-    from oracle import oracle as orc
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         orc.csr_matvec(indptr, indices, data, x)
-    reps_per_step = 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for _ in range(reps_per_step):
-            orc.csr_matvec(indptr, indices, data, x)
+        y_port = orc.csr_matvec(indptr, indices, data, x)
     el = time.perf_counter() - t0
-    value = nnz * reps_per_step * args.steps / el
+    value = nnz * args.steps / el
+    # the stock path: scipy csr_matvec, bounded to ~4 s
+    M = scipy_csr(indptr, indices, data, n)
+    y = M @ x
+    s_reps, t0 = 0, time.perf_counter()
+    while True:
+        y = M @ x
+        s_reps += 1
+        s_el = time.perf_counter() - t0
+        if s_el >= 4.0 and s_reps >= 3:
+            break
     sample = (f"{args.cpu_sample_rows} kets of the basis ({built_nnz} nnz) built by the oracle port of "
               f"get_connections+lookup, tiled with rotated columns to {nnz} nnz (DRAM-resident); "
               f"one csr_matvec over it per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(args, "cpu sample"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cores": host_threads(),
+                         "reference_scipy": {"value": nnz * s_reps / s_el, "unit": UNIT, "cores": 1, "kind": "reference",
+                                             "what": f"scipy.sparse csr_matvec (M @ x, float64) x{s_reps} in {s_el:.1f}s on the "
+                                                     "same matrix: the routine the reference's eigsh / expm_multiply call "
+                                                     "(single-threaded by construction)",
+                                             "max_abs_diff_vs_port": float(np.abs(y_port - y).max())}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "build": {"value": built_nnz / build_s, "unit": "H nnz built/s", "raw_connections_per_s": raw / build_s,
-                  "seconds": build_s, "cores": cores},
+                  "seconds": build_s, "cores": cores, "kind": "port",
+                  "reference_get_connections": reference_connections_rate(args)},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(args, l2_note):
+def workload_config(args):
+    """identical in both arms (the driver compares the dicts)"""
     n = comb(args.n_active, args.n_act_el) ** 2
     return {"workload": f"configs[3]: synthetic {args.n_orb}-orbital {args.n_alpha}+{args.n_beta}-electron "
                         f"Hamiltonian, CAS({2 * args.n_act_el}e,{args.n_active}o) window basis, {n} determinants",
-            "n_orb": args.n_orb, "n_dets": n, "flavour": "0.5*(H+H^T), FP64 values, int32 columns, CSR + SELL-32 copy for H.v",
-            "l2": l2_note}
+            "n_orb": args.n_orb, "n_dets": n, "flavour": "0.5*(H+H^T), FP64 values, int32 column ids",
+            "l2": "operator larger than the last-level cache in both arms (GPU: 26.7 GB vs 126 MB L2; CPU arm: "
+                  "DRAM-resident sample, see cpu_baseline.sample); no flush needed"}
 
 
 class CleanStdout:
@@ -408,6 +484,22 @@ def _run_ours(args, out):
             return fdist.allgather_vector(y_local, n)
         return y_local
 
+    # ---- N > 1: the fused step must reproduce the plain per-rank product + NCCL all-gather ----
+    parity = None
+    if world > 1:
+        parity = {"ok": True}
+        if fop is not None:
+            cur, worst = x.clone(), 0.0
+            for _ in range(3):                          # three ping-pong steps, unnormalised
+                ref = fdist.allgather_vector(P.matvec(cur), n)
+                got = fop.step()
+                worst = max(worst, float((got - ref).abs().max() / ref.abs().max()))
+                cur = ref
+            fop.check()
+            parity["fused_step_max_rel_diff"] = worst
+            parity["fused_step_tol"] = 1e-11
+            parity["ok"] = parity["ok"] and worst <= 1e-11
+            fop.load(x)
     for _ in range(max(args.warmup, 3)):
         step(x)
     sampler = ClockSampler(local)
@@ -571,6 +663,16 @@ def _run_ours(args, out):
         wsp = default_pt2_workspace(H, n_local_src, partition=args.pt2_partition)   # reused across sweeps
         reps = 3
         sel, imp, st = fdist.pt2_select_sharded(H, index, coeff, -30.0, 500, workspace=wsp)   # warm-up sweep
+        if world > 1:       # sharded selection == this rank's own single-GPU selection, bit for bit
+            from flow_guided_krylov_b200.expansion import pt2_select
+            ws1 = default_pt2_workspace(H, ns)
+            sel1, imp1, st1 = pt2_select(H, index, coeff, -30.0, 500, workspace=ws1)
+            same = bool(torch.equal(sel, sel1)) and bool(torch.equal(imp, imp1)) and \
+                st1["raw_candidates"] == st["raw_candidates_total"] and st1["unique_candidates"] == st["unique_total"]
+            parity["pt2_selection_equals_single_gpu"] = same
+            parity["pt2_raw_candidates"] = [st1["raw_candidates"], st["raw_candidates_total"]]
+            parity["ok"] = parity["ok"] and same
+            del ws1, sel1, imp1
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
@@ -608,22 +710,82 @@ def _run_ours(args, out):
                 "what": "fgk_conn_count + fgk_conn_fill (reference emission order, packed outputs: 28 B/connection)"}
         del od, el, srcs, offs, sample
 
+    # ---- PT2 selection at BASELINE configs[4] shape (48 orbitals, 12+12 electrons, 108,900-determinant
+    # CAS basis, 270,648 connections per source): the sharded dedup / top-k path at size ----
+    pt2_c4 = None
+    n_rows_local = P.n_rows
+    if args.pt2_c4_sources > 0:
+        del P, index, y_local, x
+        packed_copy = None
+        torch.cuda.empty_cache()
+        h1b, gb = synth_integrals(48, seed=0)
+        H48 = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1b, gb, 0.0, 24, 48, 12, 12), dev)
+        d48 = torch.from_numpy(cas_window_basis(48, 8, 11, 4).view(np.int64)).to(dev)
+        i48 = fgk.BasisIndex(d48)
+        n48 = d48.shape[0]
+        ns4 = min(args.pt2_c4_sources, n48)
+        c48 = torch.zeros(n48, dtype=torch.float64, device=dev)
+        perm = torch.randperm(n48, generator=torch.Generator().manual_seed(0))[:ns4].to(dev)
+        c48[perm] = torch.exp(-torch.arange(ns4, dtype=torch.float64, device=dev) / (0.25 * ns4))
+        c48 /= torch.linalg.norm(c48)
+        sel4, imp4, st4 = fdist.pt2_select_sharded(H48, i48, c48, -60.0, 500)      # warm-up (allocates the workspace)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        sel4, imp4, st4 = fdist.pt2_select_sharded(H48, i48, c48, -60.0, 500)
+        q1.record()
+        barrier()
+        qms = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(qms, op=dist.ReduceOp.MAX)
+        pt2_c4 = {"value": st4["raw_candidates_total"] / (float(qms[0]) * 1e-3), "unit": "PT2 candidates/s",
+                  "ms": float(qms[0]), "sources": ns4, "basis": n48, "raw_candidates": st4["raw_candidates_total"],
+                  "unique_candidates": st4["unique_total"], "passes_per_rank": st4["passes"],
+                  "selected": int(sel4.shape[0]), "top_importance": float(imp4[0]) if imp4.numel() else None,
+                  "selection_sha": __import__("hashlib").sha256(sel4.cpu().numpy().tobytes()).hexdigest()[:16],
+                  "what": "configs[4] shape, candidate space partitioned by owner rank, exact dedup, global top-500; "
+                          "1 warm-up + 1 timed selection"}
+        del H48, d48, i48, c48
+
+    if parity is not None:
+        okt = torch.tensor([1.0 if parity["ok"] else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        parity["ok"] = bool(okt[0] > 0.5)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if parity is not None and not parity["ok"]:
+            sys.exit(3)
         return
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload) ----
     cpu = None
     if not args.no_cpu_baseline:
-        indptr, indices, data, _, b_s, cores, raw, built_nnz = cpu_sample_csr(
+        cores = set_cpu_threads()
+        indptr, indices, data, _, b_s, _, raw, built_nnz = cpu_sample_csr(
             args, args.cpu_sample_rows, tile_to_nnz=int(args.cpu_step_nnz))
         rate, reps, el = cpu_spmv_rate(indptr, indices, data, n, args.cpu_seconds)
+        Msp = scipy_csr(indptr, indices, data, n)
+        xs = np.random.default_rng(1).standard_normal(n)
+        Msp @ xs
+        s_reps, t0 = 0, time.perf_counter()
+        while True:
+            Msp @ xs
+            s_reps += 1
+            s_el = time.perf_counter() - t0
+            if s_el >= 4.0 and s_reps >= 3:
+                break
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{args.cpu_sample_rows} kets of the same basis ({built_nnz} nnz, oracle-built at "
                          f"{built_nnz / b_s:.3g} H nnz/s = {raw / b_s:.3g} connections/s), tiled with rotated "
-                         f"columns to {len(data)} nnz; oracle csr_matvec x{reps} in {el:.1f}s",
-               "build_nnz_per_s": built_nnz / b_s, "connections_per_s": raw / b_s}
+                         f"columns to {len(data)} nnz; oracle csr_matvec (C/OpenMP) x{reps} in {el:.1f}s",
+               "host_cores": host_threads(),
+               "reference_scipy": {"value": len(data) * s_reps / s_el, "unit": UNIT, "cores": 1, "kind": "reference",
+                                   "what": f"scipy csr_matvec (the reference's own H.v, single-threaded) x{s_reps} in "
+                                           f"{s_el:.1f}s on the same matrix"},
+               "build_nnz_per_s": built_nnz / b_s, "connections_per_s": raw / b_s,
+               "reference_get_connections": reference_connections_rate(args)}
         # PT2 phase 1 on the CPU port: 24 sources of the same basis (single thread, like the reference's loop)
         try:
             from oracle import oracle as orc
@@ -639,7 +801,7 @@ def _run_ours(args, out):
             cpu["pt2_error"] = str(e)[:200]
 
     peak, which = measured_peak()
-    bytes_per_launch = 12.0 * nnz_local + 20.0 * P.n_rows
+    bytes_per_launch = 12.0 * nnz_local + 20.0 * n_rows_local
     achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     line = {
@@ -647,27 +809,31 @@ def _run_ours(args, out):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, "matrix (26.7 GB at full size) is larger than L2; no flush needed"),
+        "config": workload_config(args),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
+                     "frac": achieved / peak,
+                     "traffic": traffic["bytes_per_launch"] if (traffic and world == 1 and n == 1002001) else None,
                      "kernel": "k_spmv_sell<false,4>" if args.format == "sell" else "k_spmv_csr_vector<false,4>",
                      "kernel_ms": kern_ms, "csr_vector_kernel_ms": alt_ms,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": which,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,
         "e2e": {"value": nnz_total * args.steps / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * P.n_rows,
+                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n_rows_local,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "clocks": clocks,
         "gpu_launches": args.steps * (2 if fused else 1),
         "multi_gpu_step": (None if world == 1 else
                            "fused: SELL H.v storing y into every rank's next vector over NVLink peer memory + flag barrier"
                            if fused else "SELL H.v + NCCL all-gather"),
-        "build": build, "pt2": pt2, "connections": conn, "krylov": krylov, "packed_f32_storage": packed,
+        "build": build, "pt2": pt2, "pt2_config4": pt2_c4, "connections": conn, "krylov": krylov,
+        "packed_f32_storage": packed, "parity": parity,
     }
     out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 def main():
@@ -696,6 +862,8 @@ def main():
     ap.add_argument("--pt2-sources", type=int, default=2048)
     ap.add_argument("--pt2-partition", action="store_true",
                     help="PT2: radix partition (queues by top hash bits) in front of the hash map")
+    ap.add_argument("--pt2-c4-sources", type=int, default=16384,
+                    help="sources of the PT2 selection at configs[4] shape (48 orbitals); 0 disables the leg")
     ap.add_argument("--conn-dets", type=int, default=1024, help="determinants of the connection-enumeration leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=256)

@@ -489,3 +489,75 @@ FGK_HD bool ket_element_fast(const HamView& H, fgk_det ket, const Excitation& x,
     out = exc_parity_ket(ket, H.n_orb, x) ? -v : v;
     return true;
 }
+
+FGK_HD u64 fgk_double_bits(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return (u64)__double_as_longlong(v);
+#else
+    u64 b; __builtin_memcpy(&b, &v, 8); return b;
+#endif
+}
+
+// v * 2^e for a normal result (exact): builds the power of two from its exponent field
+FGK_HD double fgk_scale2(double v, int e)
+{
+    // split so that both factors are normal doubles (|e| <= 200 here)
+    const u64 b1 = (u64)(1023 + e / 2) << 52, b2 = (u64)(1023 + (e - e / 2)) << 52;
+#if defined(__CUDA_ARCH__)
+    return v * __longlong_as_double((long long)b1) * __longlong_as_double((long long)b2);
+#else
+    double p1, p2; __builtin_memcpy(&p1, &b1, 8); __builtin_memcpy(&p2, &b2, 8);
+    return v * p1 * p2;
+#endif
+}
+
+// ---- exact accumulation --------------------------------------------------------------------
+// A coupling sum  sum_j c_j <x|H|j>  is accumulated as a signed 128-bit FIXED-POINT integer
+// (resolution 2^-70, |addend| < 2^30, 27 bits of headroom for the number of addends): integer
+// addition is associative, so the sum does not depend on the order in which the warps arrive --
+// the sweep is bit-reproducible from run to run and for any number of passes / owner ranks
+// (FP64 atomicAdd in arrival order was not).  Each addend is rounded to 2^-70 once (8.5e-22,
+// far below the 1e-12 parity tolerance of the couplings); the total is converted to FP64 with
+// one correctly rounded step when the candidates are scored or exported.
+static const int PT2_FX_SHIFT = 70;
+
+FGK_HD bool fx_from_double(double v, u64& lo, u64& hi)
+{
+    const u64 bits = fgk_double_bits(v);
+    const int ex = (int)((bits >> 52) & 0x7ff);
+    lo = hi = 0;
+    if (ex == 0) return true;                           // zero / subnormal
+    const u64 mant = (bits & 0xfffffffffffffull) | (1ull << 52);
+    const int sh = ex - 1075 + PT2_FX_SHIFT;            // v = mant * 2^(ex - 1075)
+    if (sh > 47) return false;                          // |v| >= 2^30 (or inf / nan): out of range
+    if (sh >= 0) {
+        lo = mant << sh;
+        hi = sh ? mant >> (64 - sh) : 0;
+    } else if (sh > -54) {
+        lo = (mant + (1ull << (-sh - 1))) >> (-sh);     // round half up on the magnitude
+    }
+    if (bits >> 63) {                                   // two's complement negate
+        lo = ~lo + 1;
+        hi = ~hi + (lo == 0 ? 1 : 0);
+    }
+    return true;
+}
+
+FGK_HD double fx_to_double(u64 lo, u64 hi)
+{
+    const bool neg = (hi >> 63) != 0;
+    if (neg) { lo = ~lo + 1; hi = ~hi + (lo == 0 ? 1 : 0); }
+    double r;
+    if (hi == 0) {
+        r = fgk_scale2((double)lo, -PT2_FX_SHIFT);
+    } else {
+        const int lz = fgk_clz(hi);
+        u64 top = lz ? (hi << lz) | (lo >> (64 - lz)) : hi;
+        const u64 rest = lz ? (lo << lz) : lo;
+        if (rest) top |= 1ull;                          // sticky bit: one correct rounding
+        r = fgk_scale2((double)top, 64 - lz - PT2_FX_SHIFT);
+    }
+    return neg ? -r : r;
+}
+

@@ -389,4 +389,20 @@ long hc_check_split(void* h, const u64* dets, long n_dets)
     return bad;
 }
 
+// the PT2 accumulator arithmetic (fgk_pt2.cu: fx_from_double -> 128-bit integer adds with the
+// carry rule of fx_atomic_add -> fx_to_double): sum of vals[order[i]]; returns -1 if out of range
+int hc_fx_sum(const double* vals, const long* order, long n, double* out)
+{
+    u64 acc_lo = 0, acc_hi = 0;
+    for (long i = 0; i < n; i++) {
+        u64 lo, hi;
+        if (!fx_from_double(vals[order[i]], lo, hi)) return -1;
+        const u64 old = acc_lo;
+        acc_lo += lo;
+        acc_hi += hi + ((old + lo) < old ? 1ull : 0ull);
+    }
+    *out = fx_to_double(acc_lo, acc_hi);
+    return 0;
+}
+
 }  // extern "C"

@@ -11,27 +11,32 @@
 //           excitations before the full-key probe.
 // Replaces the Python dict / set of molecular.py:501,512,
 // residual_expansion.py:445-449,513 and skqd.py:171-175,405-407.
-#include <algorithm>
-#include <vector>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "fgk_internal.cuh"
 
-// The index owns ~10 small device buffers.  Plain cudaMalloc / cudaFree calls get slow (tens of
-// ms per index on some boxes) once a caching allocator holds most of the device, and an index is
-// rebuilt for every new basis; the stream-ordered allocator with an unbounded release threshold
-// keeps the blocks in the device's default pool instead.
+// The index owns ~10 small device buffers and is rebuilt for every new basis.  Plain cudaMalloc /
+// cudaFree calls get slow (tens of ms per index on some boxes) once a caching allocator holds
+// most of the device, so the buffers come from a stream-ordered memory pool OWNED BY THIS
+// LIBRARY (one per device, blocks kept between indices).  The device's default pool -- which
+// belongs to the host application -- is not touched.
 static cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st, int device)
 {
-    static bool configured[64] = {false};
-    if (!configured[device & 63]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        configured[device & 63] = true;
+    static cudaMemPool_t pools[64] = {nullptr};
+    cudaMemPool_t& pool = pools[device & 63];
+    if (!pool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess) { pool = nullptr; return e; }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    return cudaMallocAsync(p, bytes ? bytes : 16, st);
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, st);
 }
 
 static u64 pow2_at_least(u64 x)
@@ -66,32 +71,28 @@ k_index_insert(const fgk_det* __restrict__ dets, i64 n, u64* table, u64 mask)
     }
 }
 
-// insert word `which` (0 = alpha, 1 = beta) of every determinant into a word set
+// word `which` (0 = alpha, 1 = beta) of every determinant
 __global__ void __launch_bounds__(256)
-k_set_insert(const fgk_det* __restrict__ dets, i64 n, int which, u64* set, u64 mask,
-             unsigned long long* distinct)
+k_extract_words(const fgk_det* __restrict__ dets, i64 n, int which, u64* __restrict__ out)
 {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2*>(dets) + i);
-        u64 w = which ? d.y : d.x;
-        u64 slot = word_hash(w) & mask;
-        while (true) {
-            u64 prev = atomicCAS((unsigned long long*)&set[slot], FGK_EMPTY, w);
-            if (prev == FGK_EMPTY) { atomicAdd(distinct, 1ull); break; }
-            if (prev == w) break;
-            slot = (slot + 1) & mask;
-        }
+        out[i] = which ? d.y : d.x;
     }
 }
 
-// compact the occupied slots of a word set into a dense list (order irrelevant: the
-// projected-H builder sorts its rows afterwards)
+// insert the (distinct) words of a list into a word set
 __global__ void __launch_bounds__(256)
-k_set_compact(const u64* __restrict__ set, u64 size, u64* __restrict__ list, unsigned long long* counter)
+k_set_insert_list(const u64* __restrict__ list, i64 n, u64* set, u64 mask)
 {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (u64)gridDim.x * blockDim.x) {
-        u64 w = set[i];
-        if (w != FGK_EMPTY) list[atomicAdd(counter, 1ull)] = w;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const u64 w = __ldg(list + i);
+        u64 slot = word_hash(w) & mask;
+        while (true) {
+            u64 prev = atomicCAS((unsigned long long*)&set[slot], FGK_EMPTY, w);
+            if (prev == FGK_EMPTY || prev == w) break;
+            slot = (slot + 1) & mask;
+        }
     }
 }
 
@@ -137,6 +138,30 @@ static int grid1d(i64 n, int device)
     return (int)(need < cap ? need : cap);
 }
 
+static void index_release(fgk_index* I, cudaStream_t st)
+{
+    void* bufs[8] = {I->table, I->aset, I->bset, I->alist, I->blist, I->ra, I->rb, I->pair};
+    for (void* b : bufs)
+        if (b) cudaFreeAsync(b, st);
+    delete I;
+}
+
+// on a CUDA error: give every buffer back (stream-ordered) and free the handle
+#define FGK_CUDA_I(call)                                                                 \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            for (void* t__ : tmp) if (t__) cudaFreeAsync(t__, st);                       \
+            index_release(I, st);                                                        \
+            return fgk_fail(FGK_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,   \
+                            cudaGetErrorString(e__));                                    \
+        }                                                                                \
+    } while (0)
+
+// The index is complete in STREAM ORDER on `stream` when the call returns (one host
+// synchronisation inside, to size the string tables); use it on that stream, or order other
+// streams after it.  The distinct alpha / beta strings are found by a device radix sort +
+// unique (ascending lists: the projected-H builder's emission order is deterministic).
 extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, void* stream,
                                 fgk_index_t* out)
 {
@@ -146,87 +171,75 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     cudaStream_t st = (cudaStream_t)stream;
     fgk_index* I = new fgk_index();
     I->device = device;
-    I->table = I->aset = I->bset = nullptr;
+    I->stream = st;
+    I->table = I->aset = I->bset = I->alist = I->blist = nullptr;
+    I->ra = I->rb = I->pair = nullptr;
+    I->n_alpha_strings = I->n_beta_strings = 0;
+    void* tmp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // words, sorted, unique a, unique b, cub / counts
     const fgk_det* d = (const fgk_det*)dets;
     u64 tsize = pow2_at_least((u64)(n > 0 ? 2 * n : 1) < 64 ? 64 : (u64)2 * n);
-    FGK_CUDA(pool_alloc((void**)&I->table, tsize * sizeof(u64), st, device));
-    FGK_CUDA(cudaMemsetAsync(I->table, 0xFF, tsize * sizeof(u64), st));
+    FGK_CUDA_I(pool_alloc((void**)&I->table, tsize * sizeof(u64), st, device));
+    FGK_CUDA_I(cudaMemsetAsync(I->table, 0xFF, tsize * sizeof(u64), st));
+    unsigned long long h_cnt[2] = {0, 0};
     if (n > 0) {
         k_index_insert<<<grid1d(n, device), 256, 0, st>>>(d, n, I->table, tsize - 1);
-        FGK_LAUNCH_CHECK();
+        FGK_CUDA_I(cudaGetLastError());
+        // distinct strings per spin: extract -> radix sort -> unique (+ count)
+        size_t cub_a = 0, cub_b = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, cub_a, (const u64*)nullptr, (u64*)nullptr, (int)n, 0, 64, st);
+        cub::DeviceSelect::Unique(nullptr, cub_b, (const u64*)nullptr, (u64*)nullptr, (unsigned long long*)nullptr,
+                                  (int)n, st);
+        const size_t cub_bytes = ((cub_a > cub_b ? cub_a : cub_b) + 255) & ~(size_t)255;
+        for (int t = 0; t < 4; t++) FGK_CUDA_I(pool_alloc(&tmp[t], (size_t)n * sizeof(u64), st, device));
+        FGK_CUDA_I(pool_alloc(&tmp[4], cub_bytes + 2 * sizeof(unsigned long long), st, device));
+        unsigned long long* d_cnt = (unsigned long long*)((char*)tmp[4] + cub_bytes);
+        for (int which = 0; which < 2; which++) {
+            size_t tb = cub_bytes;
+            k_extract_words<<<grid1d(n, device), 256, 0, st>>>(d, n, which, (u64*)tmp[0]);
+            FGK_CUDA_I(cudaGetLastError());
+            FGK_CUDA_I(cub::DeviceRadixSort::SortKeys(tmp[4], tb, (const u64*)tmp[0], (u64*)tmp[1], (int)n, 0, 64, st));
+            tb = cub_bytes;
+            FGK_CUDA_I(cub::DeviceSelect::Unique(tmp[4], tb, (const u64*)tmp[1], (u64*)tmp[2 + which],
+                                                 d_cnt + which, (int)n, st));
+        }
+        FGK_CUDA_I(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        FGK_CUDA_I(cudaStreamSynchronize(st));          // the one host sync: sizes of the string tables
     }
-    // string sets: first pass into a worst-case table to count the distinct
-    // strings, second pass into a right-sized (cache friendly) one
-    unsigned long long* d_cnt = nullptr;
-    u64* tmp = nullptr;
-    FGK_CUDA(pool_alloc((void**)&d_cnt, 2 * sizeof(unsigned long long), st, device));
-    FGK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
-    FGK_CUDA(pool_alloc((void**)&tmp, tsize * sizeof(u64), st, device));
-    unsigned long long h_cnt[2] = {0, 0};
-    for (int which = 0; which < 2 && n > 0; which++) {
-        FGK_CUDA(cudaMemsetAsync(tmp, 0xFF, tsize * sizeof(u64), st));
-        k_set_insert<<<grid1d(n, device), 256, 0, st>>>(d, n, which, tmp, tsize - 1, d_cnt + which);
-        FGK_LAUNCH_CHECK();
-    }
-    FGK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
-    FGK_CUDA(cudaStreamSynchronize(st));
     I->n_alpha_strings = (i64)h_cnt[0];
     I->n_beta_strings = (i64)h_cnt[1];
     u64 asz = pow2_at_least(h_cnt[0] * 4 < 64 ? 64 : h_cnt[0] * 4);
     u64 bsz = pow2_at_least(h_cnt[1] * 4 < 64 ? 64 : h_cnt[1] * 4);
-    FGK_CUDA(pool_alloc((void**)&I->aset, asz * sizeof(u64), st, device));
-    FGK_CUDA(pool_alloc((void**)&I->bset, bsz * sizeof(u64), st, device));
-    FGK_CUDA(cudaMemsetAsync(I->aset, 0xFF, asz * sizeof(u64), st));
-    FGK_CUDA(cudaMemsetAsync(I->bset, 0xFF, bsz * sizeof(u64), st));
+    FGK_CUDA_I(pool_alloc((void**)&I->aset, asz * sizeof(u64), st, device));
+    FGK_CUDA_I(pool_alloc((void**)&I->bset, bsz * sizeof(u64), st, device));
+    FGK_CUDA_I(cudaMemsetAsync(I->aset, 0xFF, asz * sizeof(u64), st));
+    FGK_CUDA_I(cudaMemsetAsync(I->bset, 0xFF, bsz * sizeof(u64), st));
+    // right-sized ascending lists of the distinct strings (scanned by the projected-H builder)
+    FGK_CUDA_I(pool_alloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64), st, device));
+    FGK_CUDA_I(pool_alloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64), st, device));
     if (n > 0) {
-        k_set_insert<<<grid1d(n, device), 256, 0, st>>>(d, n, 0, I->aset, asz - 1, d_cnt);
-        FGK_LAUNCH_CHECK();
-        k_set_insert<<<grid1d(n, device), 256, 0, st>>>(d, n, 1, I->bset, bsz - 1, d_cnt + 1);
-        FGK_LAUNCH_CHECK();
-    }
-    // dense lists of the distinct strings (scanned by the projected-H builder)
-    I->alist = I->blist = nullptr;
-    FGK_CUDA(pool_alloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64), st, device));
-    FGK_CUDA(pool_alloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64), st, device));
-    FGK_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
-    if (n > 0) {
-        k_set_compact<<<grid1d((i64)asz, device), 256, 0, st>>>(I->aset, asz, I->alist, d_cnt);
-        FGK_LAUNCH_CHECK();
-        k_set_compact<<<grid1d((i64)bsz, device), 256, 0, st>>>(I->bset, bsz, I->blist, d_cnt + 1);
-        FGK_LAUNCH_CHECK();
-    }
-    FGK_CUDA(cudaStreamSynchronize(st));
-    // ascending order makes the builder's emission order deterministic (the atomic append
-    // above is not); the lists are small next to the basis, a host sort is enough
-    for (int which = 0; which < 2 && n > 0; which++) {
-        u64* dl = which ? I->blist : I->alist;
-        size_t m = (size_t)h_cnt[which];
-        std::vector<u64> hl(m);
-        FGK_CUDA(cudaMemcpy(hl.data(), dl, m * sizeof(u64), cudaMemcpyDeviceToHost));
-        std::sort(hl.begin(), hl.end());
-        FGK_CUDA(cudaMemcpy(dl, hl.data(), m * sizeof(u64), cudaMemcpyHostToDevice));
-    }
-    cudaFreeAsync(tmp, st);
-    cudaFreeAsync(d_cnt, st);
-    // rank form: string ranks per determinant and, when the basis covers at least 1/16 of its
-    // alpha x beta string product (always for CAS-like / product bases), the dense pair table
-    // the rank-based projected-H builder reads instead of probing the hash table
-    I->ra = I->rb = I->pair = nullptr;
-    if (n > 0) {
-        FGK_CUDA(pool_alloc((void**)&I->ra, (size_t)n * sizeof(int32_t), st, device));
-        FGK_CUDA(pool_alloc((void**)&I->rb, (size_t)n * sizeof(int32_t), st, device));
+        FGK_CUDA_I(cudaMemcpyAsync(I->alist, tmp[2], h_cnt[0] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        FGK_CUDA_I(cudaMemcpyAsync(I->blist, tmp[3], h_cnt[1] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        k_set_insert_list<<<grid1d((i64)h_cnt[0], device), 256, 0, st>>>(I->alist, (i64)h_cnt[0], I->aset, asz - 1);
+        FGK_CUDA_I(cudaGetLastError());
+        k_set_insert_list<<<grid1d((i64)h_cnt[1], device), 256, 0, st>>>(I->blist, (i64)h_cnt[1], I->bset, bsz - 1);
+        FGK_CUDA_I(cudaGetLastError());
+        // rank form: string ranks per determinant and, when the basis covers at least 1/16 of its
+        // alpha x beta string product (always for CAS-like / product bases), the dense pair table
+        // the rank-based projected-H builder reads instead of probing the hash table
+        FGK_CUDA_I(pool_alloc((void**)&I->ra, (size_t)n * sizeof(int32_t), st, device));
+        FGK_CUDA_I(pool_alloc((void**)&I->rb, (size_t)n * sizeof(int32_t), st, device));
         k_string_ranks<<<grid1d(n, device), 256, 0, st>>>(d, n, I->alist, I->n_alpha_strings, I->blist,
                                                           I->n_beta_strings, I->ra, I->rb);
-        FGK_LAUNCH_CHECK();
+        FGK_CUDA_I(cudaGetLastError());
         const i64 prod = I->n_alpha_strings * I->n_beta_strings;
         const i64 lim = 16 * n > (1ll << 20) ? 16 * n : (1ll << 20);
         if (prod <= lim && prod < (1ll << 31)) {
-            FGK_CUDA(pool_alloc((void**)&I->pair, (size_t)prod * sizeof(int32_t), st, device));
-            FGK_CUDA(cudaMemsetAsync(I->pair, 0xFF, (size_t)prod * sizeof(int32_t), st));
+            FGK_CUDA_I(pool_alloc((void**)&I->pair, (size_t)prod * sizeof(int32_t), st, device));
+            FGK_CUDA_I(cudaMemsetAsync(I->pair, 0xFF, (size_t)prod * sizeof(int32_t), st));
             k_pair_fill<<<grid1d(n, device), 256, 0, st>>>(I->ra, I->rb, n, I->n_beta_strings, I->pair);
-            FGK_LAUNCH_CHECK();
+            FGK_CUDA_I(cudaGetLastError());
         }
-        FGK_CUDA(cudaStreamSynchronize(st));
+        for (void*& t : tmp) { if (t) cudaFreeAsync(t, st); t = nullptr; }
     }
     I->v.ra = I->ra; I->v.rb = I->rb; I->v.pair = I->pair; I->v.n_bstr = I->n_beta_strings;
     I->v.dets = d; I->v.n = n;
@@ -236,18 +249,16 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     *out = I;
     return FGK_OK;
 }
+#undef FGK_CUDA_I
 
+// The buffers go back to the library's pool in stream order on the stream the index was created
+// on: work queued on that stream before the call still sees them (no device-wide
+// synchronisation).  Work on OTHER streams must have been ordered before this call by the caller.
 extern "C" int fgk_index_destroy(fgk_index_t idx)
 {
     if (!idx) return FGK_OK;
     cudaSetDevice(idx->device);
-    // same guarantee as cudaFree (no kernel on any stream still reads the tables), but the blocks
-    // go back to the pool instead of the driver
-    cudaDeviceSynchronize();
-    void* bufs[8] = {idx->table, idx->aset, idx->bset, idx->alist, idx->blist, idx->ra, idx->rb, idx->pair};
-    for (void* b : bufs)
-        if (b) cudaFreeAsync(b, 0);
-    delete idx;
+    index_release(idx, idx->stream);
     return FGK_OK;
 }
 

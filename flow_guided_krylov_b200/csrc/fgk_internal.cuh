@@ -62,6 +62,7 @@ struct IndexView {
 
 struct fgk_index {
     int device;
+    cudaStream_t stream;            // creation stream: the buffers are freed in its order
     IndexView v;
     u64 *table, *aset, *bset;
     u64 *alist, *blist;             // the distinct alpha / beta strings, ascending
@@ -72,7 +73,7 @@ struct fgk_index {
 struct Pt2View {
     u64* table;         // (tag << 32 | slot), empty = ~0
     u64 mask;           // table_slots - 1
-    u64* pool;          // 4 words per slot: {alpha, beta, FP64 accumulator bits, spare}
+    u64* pool;          // 4 words per slot: {alpha, beta, accumulator lo, hi} (128-bit fixed point; MAXABS: FP64 bits, 0)
     i64 capacity;
     unsigned long long* counters;   // [0] slots used, [1] raw candidates tested, [2] overflow
     // The table is split into 2^region_bits regions selected by the TOP hash bits; linear
@@ -92,6 +93,8 @@ struct Pt2View {
 struct fgk_pt2 {
     int device;
     Pt2View v;
+    int mode;           // FGK_PT2_SUM / FGK_PT2_MAXABS of the sweep in progress, -1 after reset
+    bool scored;        // accumulators already converted to {coupling, score} by fgk_pt2_score
 };
 
 static const u64 FGK_EMPTY = ~0ull;

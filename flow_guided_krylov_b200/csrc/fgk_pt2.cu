@@ -12,19 +12,25 @@
 
 #include "fgk_internal.cuh"
 
-__device__ __forceinline__ void atomic_max_abs(double* addr, double v)
+// exact accumulation: fx_from_double / fx_to_double live in fgk_core.cuh (shared with the CPU self-check)
+__device__ __forceinline__ void fx_atomic_add(u64* acc, u64 lo, u64 hi)
 {
-    // non-negative doubles order like their bit patterns
-    atomicMax(reinterpret_cast<unsigned long long*>(addr),
-              (unsigned long long)__double_as_longlong(fabs(v)));
+    const u64 old = atomicAdd((unsigned long long*)acc, (unsigned long long)lo);
+    const u64 add_hi = hi + ((old + lo) < old ? 1ull : 0ull);      // carry out of the low word
+    if (add_hi) atomicAdd((unsigned long long*)(acc + 1), (unsigned long long)add_hi);
 }
 
 // insert-or-accumulate; returns false on pool overflow.
-// Pool entry = 32 bytes {alpha, beta, FP64 accumulator, spare}: the key compare and the
-// accumulation of a repeat candidate touch ONE 32-byte sector (two with separate key / sum
-// arrays -- the sweep is bound by random DRAM sectors).  A new entry is written complete,
-// first contribution included, before the table slot is published, so the pool needs no
-// clearing between sweeps and a new candidate costs no accumulator atomic.
+// Pool entry = 32 bytes {alpha, beta, accumulator lo, accumulator hi}: the key compare and the
+// accumulation of a repeat candidate touch ONE 32-byte sector (the sweep is bound by random
+// DRAM sectors).  Publication protocol: the thread that wins the table slot (CAS empty ->
+// tag|LOCKED) is the only one that claims a pool entry; it writes the entry complete, first
+// contribution included, and then stores tag|slot.  A thread that meets tag|LOCKED with its own
+// tag waits for the publication.  So a pass needs exactly one pool entry per DISTINCT candidate
+// (a loser of the race used to burn one per simultaneous duplicate), the pool needs no clearing
+// between sweeps and a new candidate costs no accumulator atomic.
+static const unsigned PT2_LOCKED = 0xFFFFFFFEu, PT2_TOMB = 0xFFFFFFFDu;
+
 __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, double val, int mode)
 {
     const u64 tag = h >> 32;
@@ -32,43 +38,47 @@ __device__ __forceinline__ bool pt2_upsert(const Pt2View& W, fgk_det o, u64 h, d
     u64 local = (h >> 7) & W.region_mask;
     u64 slot = base + local;
     u64 probes = 0;
-    long long mine = -1;        // pool slot this thread allocated (at most one)
-    bool ok = true;
+    u64 lo, hi = 0;
+    if (mode == FGK_PT2_MAXABS) lo = (u64)__double_as_longlong(fabs(val));
+    else if (!fx_from_double(val, lo, hi)) { atomicExch(W.counters + 2, 2ull); return false; }
     while (true) {
-        if (++probes > W.region_mask + 1) { atomicExch(W.counters + 2, 1ull); ok = false; break; }   // region full
-        u64 e = *reinterpret_cast<volatile u64*>(W.table + slot);
+        if (++probes > W.region_mask + 1) { atomicExch(W.counters + 2, 1ull); return false; }   // region full
+        volatile u64* ts = reinterpret_cast<volatile u64*>(W.table + slot);
+        u64 e = *ts;
         if (e == FGK_EMPTY) {
-            if (mine < 0) {
-                mine = (long long)atomicAdd(W.counters, 1ull);
-                if (mine >= W.capacity) { atomicExch(W.counters + 2, 1ull); ok = false; break; }
+            const u64 prev = atomicCAS((unsigned long long*)(W.table + slot), FGK_EMPTY,
+                                       (tag << 32) | (u64)PT2_LOCKED);
+            if (prev == FGK_EMPTY) {
+                const u64 mine = atomicAdd(W.counters, 1ull);
+                if (mine >= (u64)W.capacity) {
+                    atomicExch(W.counters + 2, 1ull);
+                    *ts = (tag << 32) | (u64)PT2_TOMB;          // release the waiters
+                    return false;
+                }
                 ulonglong2* p = reinterpret_cast<ulonglong2*>(W.pool + 4 * mine);
-                const double v0 = mode == FGK_PT2_MAXABS ? fabs(val) : val;
                 p[0] = make_ulonglong2(o.a, o.b);
-                p[1] = make_ulonglong2((u64)__double_as_longlong(v0), 0ull);
+                p[1] = make_ulonglong2(lo, hi);
                 __threadfence();
+                *ts = (tag << 32) | mine;                        // publish, contribution inside
+                return true;
             }
-            u64 prev = atomicCAS((unsigned long long*)(W.table + slot), FGK_EMPTY,
-                                 (tag << 32) | (u64)(unsigned)mine);
-            if (prev == FGK_EMPTY) { mine = -1; break; }      // published, contribution inside
             e = prev;               // somebody else took the slot: inspect it
         }
         if ((e >> 32) == tag) {
-            unsigned ps = (unsigned)(e & 0xffffffffu);
-            // L2 read: the entry was published with __threadfence before the CAS
-            u64* p = W.pool + 4 * (u64)ps;
-            ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(p));
+            while ((unsigned)e == PT2_LOCKED) e = *ts;          // entry being written
+            if ((unsigned)e == PT2_TOMB) return false;
+            // L2 read: the entry was completed with __threadfence before the publishing store
+            u64* p = W.pool + 4 * (e & 0xffffffffull);
+            const ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(p));
             if (k.x == o.a && k.y == o.b) {
-                if (mode == FGK_PT2_MAXABS) atomic_max_abs(reinterpret_cast<double*>(p + 2), val);
-                else atomicAdd(reinterpret_cast<double*>(p + 2), val);
-                break;
+                if (mode == FGK_PT2_MAXABS) atomicMax((unsigned long long*)(p + 2), (unsigned long long)lo);
+                else fx_atomic_add(p + 2, lo, hi);
+                return true;
             }
         }
         local = (local + 1) & W.region_mask;
         slot = base + local;
     }
-    if (mine >= 0 && mine < W.capacity)   // allocated but lost the race: mark the slot dead
-        *reinterpret_cast<ulonglong2*>(W.pool + 4 * mine) = make_ulonglong2(FGK_EMPTY, FGK_EMPTY);
-    return ok;
 }
 
 // work unit = (source, split): the 32-wide index chunks of one source's excitation
@@ -359,7 +369,7 @@ k_pt2_aggregate(Pt2View W, int mode, i64 per_block)
 // live candidates are compacted to the front of the outputs (order is not
 // deterministic; every consumer treats them as a set); counters[3] = live count.
 __global__ void __launch_bounds__(1024)
-k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, double energy,
+k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, double energy, bool fixed_point,
              fgk_det* __restrict__ out_dets, double* __restrict__ out_coupling,
              double* __restrict__ out_diag, double* __restrict__ out_importance)
 {
@@ -396,7 +406,7 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
         base = __shfl_sync(0xffffffffu, base, 0);
         if (!live) continue;
         const i64 o = (i64)base + __popc(b & ((1u << lane) - 1u));
-        const double cpl = __longlong_as_double((long long)acc.x);
+        const double cpl = fixed_point ? fx_to_double(acc.x, acc.y) : __longlong_as_double((long long)acc.x);
         if (out_dets) reinterpret_cast<ulonglong2*>(out_dets)[o] = d;
         if (out_coupling) out_coupling[o] = cpl;
         if (have_h) {
@@ -420,7 +430,7 @@ k_pt2_export(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots,
 static const int PT2_BINS = 2048;      // sign + 11 exponent bits of a non-negative double
 
 __global__ void __launch_bounds__(1024)
-k_pt2_score(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, double energy,
+k_pt2_score(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, double energy, bool fixed_point,
             unsigned* __restrict__ hist)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -443,7 +453,9 @@ k_pt2_score(HamView H, bool have_h, unsigned tab_bytes, Pt2View W, i64 n_slots, 
         const ulonglong2 d = p[0];
         if (d.x == FGK_EMPTY && d.y == FGK_EMPTY) continue;
         ulonglong2 acc = p[1];
-        const double cpl = __longlong_as_double((long long)acc.x);
+        // the accumulator becomes {coupling (FP64), score}: the sweep is complete when it is scored
+        const double cpl = fixed_point ? fx_to_double(acc.x, acc.y) : __longlong_as_double((long long)acc.x);
+        acc.x = (u64)__double_as_longlong(cpl);
         double score = fabs(cpl);
         if (have_h) {
             fgk_det dd = {d.x, d.y};
@@ -533,7 +545,8 @@ extern "C" int fgk_pt2_score(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double 
     FGK_CUDA(cudaMemsetAsync(hist, 0, PT2_BINS * sizeof(unsigned), st));
     i64 need = (n_slots + 1023) / 1024, cap = (i64)fgk_sm_count(ws->device) * 2;
     k_pt2_score<<<(int)(need < cap ? need : cap), 1024, tab_bytes, st>>>(
-        hv, h != nullptr, tab_bytes, ws->v, n_slots, energy, (unsigned*)hist);
+        hv, h != nullptr, tab_bytes, ws->v, n_slots, energy, ws->mode == FGK_PT2_SUM && !ws->scored, (unsigned*)hist);
+    ws->scored = true;
     FGK_LAUNCH_CHECK();
     k_pt2_threshold<<<1, 32, 0, st>>>((const unsigned*)hist, k, (unsigned long long*)thr);
     FGK_LAUNCH_CHECK();
@@ -576,12 +589,14 @@ extern "C" int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* t
 {
     if (!out || capacity < 1 || !table || !pool || !counters)
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: bad argument");
-    if (capacity >= (1ll << 32) - 1) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_pt2_create: capacity >= 2^32");
+    if (capacity >= (1ll << 32) - 4) return fgk_fail(FGK_ERR_UNSUPPORTED, "fgk_pt2_create: capacity >= 2^32 - 4");
     if (table_slots < 2 || (table_slots & (table_slots - 1)) || table_slots < capacity)
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: table_slots must be a power of two >= capacity");
     if ((uintptr_t)pool & 31) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_create: pool must be 32-byte aligned");
     fgk_pt2* P = new fgk_pt2();
     P->device = device;
+    P->mode = -1;
+    P->scored = false;
     P->v.capacity = capacity;
     P->v.mask = (u64)table_slots - 1;
     P->v.table = (u64*)table;
@@ -636,6 +651,8 @@ extern "C" int fgk_pt2_reset(fgk_pt2_t ws, void* stream)
     FGK_CUDA(cudaMemsetAsync(ws->v.counters, 0, 4 * sizeof(unsigned long long), st));
     if (ws->v.queue_bits)
         FGK_CUDA(cudaMemsetAsync(ws->v.qcursors, 0, sizeof(unsigned long long) << ws->v.queue_bits, st));
+    ws->mode = -1;
+    ws->scored = false;
     return FGK_OK;
 }
 
@@ -649,6 +666,11 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: bad argument");
     if (h->device != idx->device || h->device != ws->device)
         return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: device mismatch");
+    if (mode != FGK_PT2_SUM && mode != FGK_PT2_MAXABS) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: bad mode");
+    if (ws->scored || (ws->mode >= 0 && ws->mode != mode))
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_accumulate: workspace already scored or used in the other mode "
+                                     "(call fgk_pt2_reset first)");
+    ws->mode = mode;
     FGK_CUDA(cudaSetDevice(h->device));
     const i64 resident_warps = (i64)fgk_sm_count(h->device) * 64;
     i64 n_split = (4 * resident_warps + n_src - 1) / n_src;     // >= 4 waves of work units
@@ -722,6 +744,10 @@ extern "C" int fgk_pt2_merge(fgk_pt2_t ws, const uint64_t* dets, const double* v
     if (!ws) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_merge: null handle");
     if (m == 0) return FGK_OK;
     if (!dets || !vals || m < 0) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_merge: bad argument");
+    if (mode != FGK_PT2_SUM && mode != FGK_PT2_MAXABS) return fgk_fail(FGK_ERR_ARG, "fgk_pt2_merge: bad mode");
+    if (ws->scored || (ws->mode >= 0 && ws->mode != mode))
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2_merge: workspace already scored or used in the other mode");
+    ws->mode = mode;
     FGK_CUDA(cudaSetDevice(ws->device));
     i64 need = (m + 255) / 256, cap = (i64)fgk_sm_count(ws->device) * 8;
     k_pt2_merge<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
@@ -742,6 +768,8 @@ extern "C" int fgk_pt2_count(fgk_pt2_t ws, void* stream, int64_t* n_slots, int64
     if (n_slots) *n_slots = used;
     if (n_raw) *n_raw = (i64)hc[1];
     if (overflow) *overflow = hc[2] ? 1 : 0;
+    if (hc[2] == 2)
+        return fgk_fail(FGK_ERR_ARG, "fgk_pt2: a coupling c_j <x|H|j> is not finite or exceeds 2^30");
     if (hc[2])
         return fgk_fail(FGK_ERR_CAPACITY, "fgk_pt2: candidate pool overflow (capacity %lld)",
                         (long long)ws->v.capacity);
@@ -768,7 +796,8 @@ extern "C" int fgk_pt2_export(fgk_ham_t h, fgk_pt2_t ws, int64_t n_slots, double
     cudaStream_t st = (cudaStream_t)stream;
     FGK_CUDA(cudaMemsetAsync(ws->v.counters + 3, 0, sizeof(unsigned long long), st));
     k_pt2_export<<<(int)(need < cap ? need : cap), 1024, tab_bytes, st>>>(
-        hv, h != nullptr, tab_bytes, ws->v, n_slots, energy, (fgk_det*)out_dets, out_coupling, out_diag,
+        hv, h != nullptr, tab_bytes, ws->v, n_slots, energy, ws->mode == FGK_PT2_SUM && !ws->scored,
+        (fgk_det*)out_dets, out_coupling, out_diag,
         out_importance);
     FGK_LAUNCH_CHECK();
     unsigned long long live = 0;

@@ -201,10 +201,10 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
     the multi-GPU split -- the significant sources, not the rows, are what must balance).
     Returns (cand_dets, coupling, diag, importance, stats).
 
-    Pool slots are claimed before the table slot is won, so threads that meet the same new
-    candidate at the same time each use one (the losers' slots are marked dead): a pass needs
-    room for up to its RAW candidates in the worst case, which is what default_pt2_capacity
-    provides; an undersized workspace just takes more passes."""
+    A pass needs one pool entry per DISTINCT candidate (the table slot is won before a pool
+    entry is claimed); an undersized workspace just takes more bucket passes.  Coupling sums are
+    exact 128-bit fixed-point accumulations: bit-identical from run to run, for any number of
+    passes and any number of owner ranks."""
     dev = ham.device
     n = len(index)
     c32 = coeffs.to(dev).to(torch.float32)                         # :481
@@ -247,13 +247,18 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
 
 
 def default_pt2_capacity(ham, n_sources, partition=False):
-    """distinct-candidate capacity for a sweep over n_sources determinants: every raw
-    connection could be a distinct candidate; bounded by the free HBM.  Per unit of capacity:
-    16 B table + 32 B pool + 24 B export buffers, plus 2 x 30 B of partition queue."""
+    """distinct-candidate capacity for a sweep over n_sources determinants.  Small sweeps: every
+    raw connection could be a distinct candidate.  Large sweeps: half of the raw connections
+    (measured 0.37 distinct per raw connection on the configs[3] sweep, 0.2 on configs[4]); a
+    sweep that does not fit is split into bucket passes by the callers.  Bounded by the free HBM;
+    per unit of capacity: 16 B table + 32 B pool + 24 B head buffers, plus 2 x 30 B of partition
+    queue."""
     n_conn = _raw_connections_per_det(ham)
+    raw = n_sources * n_conn
+    want = raw if raw <= (1 << 24) else max(1 << 24, raw // 2)
     free = nat.device_info(ham.device)["free_bytes"]
     per = 72 + (60 if partition else 0) + 8
-    return int(min(max(4096, 1.05 * n_sources * n_conn), 0.8 * free / per, 2 ** 31))
+    return int(min(max(4096, 1.05 * want), 0.8 * free / per, 2 ** 32 - 8))
 
 
 def default_pt2_workspace(ham, n_sources, partition=False):

@@ -110,7 +110,10 @@ int fgk_conn_fill(fgk_ham_t h, const uint64_t* dets, int64_t n, const int64_t* o
  * `dets` must stay alive and unchanged while the index is used (the table stores
  * indices into it).  Duplicate determinants resolve to the LAST index, like the
  * reference's dict comprehension.  Synchronises `stream` once (to size the
- * alpha/beta string sets). */
+ * alpha/beta string sets); the index is complete in stream order on `stream`.  Its device
+ * buffers come from a stream-ordered memory pool owned by the library (the device's default
+ * pool is not touched); fgk_index_destroy returns them in the order of the creation stream,
+ * without a device-wide synchronisation.  On error nothing is leaked. */
 int fgk_index_create(const uint64_t* dets, int64_t n, int device, void* stream, fgk_index_t* out);
 int fgk_index_destroy(fgk_index_t idx);
 /* out_idx[k] = position of query[k] in the basis, or -1 */
@@ -204,12 +207,16 @@ int fgk_peer_barrier(uint64_t* const* peer_flags, int rank, int world, uint64_t 
 /* ---- K7/K8 PT2 residual expansion --------------------------------------------------------
  * replaces SelectedCIExpander._find_important_configs (residual_expansion.py:451-554)
  * and ResidualBasedExpander._find_residual_configs (:174-253).
- * The workspace is a device hash map determinant -> FP64 accumulator with room for
- * `capacity` distinct candidates.  All of its memory is the caller's:
+ * The workspace is a device hash map determinant -> accumulator with room for
+ * `capacity` distinct candidates (one pool entry per DISTINCT candidate of a pass, however
+ * many sources reach it at the same time).  All of its memory is the caller's:
  *   table    uint64[table_slots]   (table_slots a power of two, >= 2*capacity advised)
- *   pool     uint64[capacity][4]   (32-byte aligned; one entry = {alpha, beta, FP64
- *                                   accumulator, spare}: key and sum share a 32-byte sector)
+ *   pool     uint64[capacity][4]   (32-byte aligned; one entry = {alpha, beta, accumulator lo,
+ *                                   hi}: key and sum share a 32-byte sector)
  *   counters uint64[4]
+ * SUM mode accumulates in signed 128-bit fixed point (2^-70 resolution, |addend| < 2^30):
+ * integer adds are associative, so coupling sums are bit-identical from run to run and for
+ * any split into passes / owner ranks; they become FP64 (one rounding) in score / export.
  * fgk_pt2_create only wraps them in a handle; call fgk_pt2_reset before use (it clears the
  * table and the counters; pool entries are written complete when they are claimed). */
 int fgk_pt2_create(int64_t capacity, int64_t table_slots, uint64_t* table, uint64_t* pool,
@@ -241,8 +248,9 @@ int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, const int64_t
 /* merge externally produced (determinant, value) pairs (multi-GPU dedup exchange) */
 int fgk_pt2_merge(fgk_pt2_t ws, const uint64_t* dets, const double* vals, int64_t m, int mode,
                   void* stream);
-/* synchronises; host outputs: number of pool slots used (incl. dead ones), raw
- * candidates tested so far, overflow flag.  Returns FGK_ERR_CAPACITY on overflow. */
+/* synchronises; host outputs: number of pool slots used (= distinct candidates), raw
+ * candidates tested so far, overflow flag.  Returns FGK_ERR_CAPACITY on overflow, FGK_ERR_ARG
+ * if an addend was not finite or >= 2^30 in magnitude. */
 int fgk_pt2_count(fgk_pt2_t ws, void* stream, int64_t* n_slots, int64_t* n_raw, int* overflow);
 /* The live candidates among the first n_slots pool slots, COMPACTED to the front of
  * the outputs (buffers sized n_slots; order unspecified): determinant, accumulated

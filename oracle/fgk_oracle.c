@@ -46,6 +46,16 @@ typedef struct {
 #define G4(H, p, q, r, s) \
     ((H)->g[(((size_t)(p) * (H)->n_orb + (q)) * (H)->n_orb + (r)) * (H)->n_orb + (s)])
 
+/* the harness sets the thread count itself: torchrun exports OMP_NUM_THREADS=1 to its workers */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -42,6 +42,7 @@ def lib():
         L.orc_ham_create.argtypes = [vp, vp, ci, dbl]
         L.orc_ham_destroy.argtypes = [vp]
         L.orc_num_threads.restype = ci
+        L.orc_set_num_threads.argtypes = [ci]
         L.orc_sign_single.restype = ci
         L.orc_sign_single.argtypes = [vp, ci, ci]
         L.orc_sign_double.restype = ci

@@ -79,5 +79,7 @@ def hostcheck():
         L.hc_pt2_walk2.argtypes = [vp, u64, u64, vp, vp, i64]
         L.hc_check_split.restype = i64
         L.hc_check_split.argtypes = [vp, vp, i64]
+        L.hc_fx_sum.restype = ci
+        L.hc_fx_sum.argtypes = [vp, vp, i64, vp]
         _hc = L
     return _hc

@@ -273,3 +273,44 @@ def test_random_shapes_against_oracle(seed):
             off = ~np.eye(n, dtype=bool)
             assert np.array_equal(got[off], ref[off])
     hostcheck().hc_ham_destroy(hc)
+
+
+def test_pt2_fixed_point_accumulator_is_exact_and_order_independent():
+    """fgk_pt2.cu accumulates couplings as 128-bit fixed point (fx_from_double / fx_atomic_add /
+    fx_to_double): any order gives the same bits, and the result is the correctly rounded sum of
+    the addends (each rounded to 2^-70 first)."""
+    import math
+    from fractions import Fraction
+    L = hostcheck()
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        n = int(rng.integers(1, 4000))
+        scale = 10.0 ** rng.integers(-14, 6)
+        v = (rng.standard_normal(n) * scale * 10.0 ** rng.integers(-6, 1, n)).astype(np.float64)
+        if trial % 4 == 0:
+            v[: n // 2] = -v[n // 2: 2 * (n // 2)][::-1]        # heavy cancellation
+        outs = []
+        for perm in (np.arange(n), np.arange(n)[::-1].copy(), rng.permutation(n)):
+            out = np.zeros(1)
+            perm = np.ascontiguousarray(perm, dtype=np.int64)
+            assert L.hc_fx_sum(v.ctypes.data, perm.ctypes.data, n, out.ctypes.data) == 0
+            outs.append(out[0])
+        assert outs[0].tobytes() == outs[1].tobytes() == outs[2].tobytes()
+        # exact reference: every addend rounded to a multiple of 2^-70 (half away from zero), exact rational sum
+        q = Fraction(1, 2 ** 70)
+        tot = Fraction(0)
+        for x in v:
+            fx = Fraction(float(x)) / q
+            r = math.floor(abs(fx) + Fraction(1, 2))
+            tot += (r if fx >= 0 else -r) * q
+        assert outs[0] == float(tot)                           # float(Fraction) rounds correctly
+        assert abs(outs[0] - math.fsum(v)) <= 1e-20 * n + 4e-16 * abs(math.fsum(v))
+    # range guard: |v| >= 2^30, inf, nan are refused
+    for bad in (2.0 ** 30, -1e12, np.inf, np.nan):
+        out = np.zeros(1)
+        one = np.zeros(1, np.int64)
+        assert L.hc_fx_sum(np.array([bad]).ctypes.data, one.ctypes.data, 1, out.ctypes.data) == -1
+    out = np.zeros(1)
+    one = np.zeros(1, np.int64)
+    assert L.hc_fx_sum(np.array([2.0 ** 30 - 1.0]).ctypes.data, one.ctypes.data, 1, out.ctypes.data) == 0
+    assert out[0] == 2.0 ** 30 - 1.0
