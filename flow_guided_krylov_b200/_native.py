@@ -16,6 +16,7 @@ _lib = None
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 H_RAW, H_SYM, H_DROP_ZEROS, H_FLAT_WALK, H_HASH_WALK = 0, 1, 2, 4, 8
 PT2_SUM, PT2_MAXABS = 0, 1
+PEER_COMPLEX, PEER_PACKED_F32 = 1, 2
 
 vp, i64, ci, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
 
@@ -54,6 +55,9 @@ _SIGNATURES = {
     "fgk_peer_free": (ci, [vp, ci]),
     "fgk_spmv_sell_f64_allgather": (ci, [i64, vp, vp, vp, vp, C.POINTER(vp), ci, i64, ci, vp]),
     "fgk_peer_barrier": (ci, [C.POINTER(vp), ci, ci, C.c_uint64, vp, ci, vp]),
+    "fgk_peer_step": (ci, [i64, vp, vp, vp, vp, vp, C.POINTER(vp), ci, i64, C.POINTER(vp), ci, ci, C.c_uint64,
+                           vp, vp, ci, vp]),
+    "fgk_peer_gather": (ci, [vp, i64, C.POINTER(vp), i64, C.POINTER(vp), ci, ci, C.c_uint64, vp, vp, ci, vp]),
     "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, ci, C.POINTER(vp)]),
     "fgk_pt2_destroy": (ci, [vp]),
     "fgk_pt2_set_partition": (ci, [vp, ci, ci, i64, vp, vp, vp]),

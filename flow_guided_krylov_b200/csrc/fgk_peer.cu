@@ -149,6 +149,230 @@ __global__ void k_peer_barrier(const __grid_constant__ PeerFlags F, int rank, in
     }
 }
 
+
+// ======================================================================================
+// One-launch step: product + broadcast + barrier.
+// k_peer_step is the same product (FP64 SELL-32 or packed exact-float32 SELL-32 storage, real or
+// complex vector); every CTA stores its 32 rows into the NEXT vector of every rank, fences
+// (system scope) and bumps a device counter; the CTA that finishes LAST performs the flag
+// barrier that k_peer_barrier used to do in a second launch: arrive on every rank's flag array,
+// then wait until every peer has arrived.  When the kernel completes, the next vector is
+// complete on this rank and every peer has finished reading the current one.
+// One CTA per GPU waits, and the ranks' kernels run on different GPUs: no co-residency
+// assumption between launches.
+// ======================================================================================
+__device__ __forceinline__ uint4 ldp_u32x4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+struct PeerSync {
+    unsigned long long* f[PEER_MAX];    // flag arrays (see k_peer_barrier)
+    unsigned* done;                     // device counter of finished CTAs (self-resetting)
+    unsigned long long* err;
+    unsigned long long epoch;
+    int rank, world;
+};
+
+// called by every thread of every CTA after its remote stores; one warp of the last CTA runs the barrier
+__device__ __forceinline__ void peer_finish(const PeerSync& S)
+{
+    __shared__ bool s_last;
+    __threadfence_system();                       // my remote stores are visible system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(S.done, 1u);
+        s_last = prev == gridDim.x * gridDim.y - 1;
+        if (s_last) *S.done = 0;                  // ready for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();                       // every CTA's stores happened before its counter bump
+    const int p = threadIdx.x;
+    if (p < S.world) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(S.f[p] + S.rank), "l"(S.epoch) : "memory");
+        unsigned long long seen = 0;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(S.f[S.rank] + p) : "memory");
+            if (++spins > 400000000ll) { *S.err = S.epoch; break; }
+        } while (seen < S.epoch);
+    }
+}
+
+template <bool CPLX, bool PACKED, int UNROLL>
+__global__ void __launch_bounds__(128, CPLX ? 10 : 14)
+k_peer_step(i64 n_rows, const i64* __restrict__ slice_ptr, const void* __restrict__ cols_or_packed,
+            const double* __restrict__ vals, const double* __restrict__ diag, const double* __restrict__ x,
+            const __grid_constant__ PeerPtrs P, const __grid_constant__ PeerSync S, i64 row_offset)
+{
+    __shared__ double s_part[4][32][CPLX ? 2 : 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const i64 s = blockIdx.x;
+    const i64 base = __ldg(slice_ptr + s);
+    double re = 0.0, im = 0.0;
+    auto add = [&](double v, int c) {
+        if (CPLX) {
+            const double2 z = __ldg(reinterpret_cast<const double2*>(x) + c);
+            re = fma(v, z.x, re);
+            im = fma(v, z.y, im);
+        } else {
+            re = fma(v, __ldg(x + c), re);
+        }
+    };
+    if (PACKED) {
+        const i64 npair = (__ldg(slice_ptr + s + 1) - base) >> 5;          // slice_ptr in 16-byte units
+        const uint4* p0 = reinterpret_cast<const uint4*>(cols_or_packed) + base + lane;
+        i64 k2 = w;
+        for (; k2 + 4ll * (UNROLL - 1) < npair; k2 += 4ll * UNROLL) {
+            uint4 q[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) q[u] = ldp_u32x4(p0 + (k2 + 4ll * u) * 32);
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                add((double)__uint_as_float(q[u].x), (int)q[u].z);
+                add((double)__uint_as_float(q[u].y), (int)q[u].w);
+            }
+        }
+        for (; k2 < npair; k2 += 4) {
+            const uint4 q = ldp_u32x4(p0 + k2 * 32);
+            add((double)__uint_as_float(q.x), (int)q.z);
+            add((double)__uint_as_float(q.y), (int)q.w);
+        }
+    } else {
+        const i64 npair = (__ldg(slice_ptr + s + 1) - base) >> 6;
+        const double* v0 = vals + base + 2 * lane;
+        const int32_t* c0 = reinterpret_cast<const int32_t*>(cols_or_packed) + base + 2 * lane;
+        i64 k2 = w;
+        for (; k2 + 4ll * (UNROLL - 1) < npair; k2 += 4ll * UNROLL) {
+            double2 v[UNROLL];
+            int2 c[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                v[u] = ldp_f64x2(v0 + (k2 + 4ll * u) * 64);
+                c[u] = ldp_s32x2(c0 + (k2 + 4ll * u) * 64);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) { add(v[u].x, c[u].x); add(v[u].y, c[u].y); }
+        }
+        for (; k2 < npair; k2 += 4) {
+            const double2 v = ldp_f64x2(v0 + k2 * 64);
+            const int2 c = ldp_s32x2(c0 + k2 * 64);
+            add(v.x, c.x);
+            add(v.y, c.y);
+        }
+    }
+    s_part[w][lane][0] = re;
+    if (CPLX) s_part[w][lane][CPLX ? 1 : 0] = im;
+    __syncthreads();
+    const i64 r = s * 32 + lane;
+    if (r < n_rows) {
+        double yr = s_part[0][lane][0] + s_part[1][lane][0] + s_part[2][lane][0] + s_part[3][lane][0];
+        double yi = 0.0;
+        if (CPLX) yi = s_part[0][lane][CPLX ? 1 : 0] + s_part[1][lane][CPLX ? 1 : 0] +
+                       s_part[2][lane][CPLX ? 1 : 0] + s_part[3][lane][CPLX ? 1 : 0];
+        if (PACKED) {                             // the diagonal lives in its own FP64 array
+            const double dg = __ldg(diag + r);
+            if (CPLX) {
+                const double2 xr = __ldg(reinterpret_cast<const double2*>(x) + row_offset + r);
+                yr = fma(dg, xr.x, yr);
+                yi = fma(dg, xr.y, yi);
+            } else {
+                yr = fma(dg, __ldg(x + row_offset + r), yr);
+            }
+        }
+        // warp w serves peers w, w+4, ...: one coalesced 256-byte (512-byte) store per peer
+        for (int p = w; p < S.world; p += 4) {
+            if (CPLX) reinterpret_cast<double2*>(P.out[p])[row_offset + r] = make_double2(yr, yi);
+            else P.out[p][row_offset + r] = yr;
+        }
+    }
+    peer_finish(S);
+}
+
+// all-gather of a vector whose row block lives on this rank: src[0 .. n_local) (16-byte words)
+// -> dst_p[dst_offset + i] on every rank p, then the same last-CTA barrier.  Used to distribute
+// the INPUT of a product (row-sharded Krylov vectors; host vectors uploaded in N slices).
+__global__ void __launch_bounds__(256)
+k_peer_gather(const double* __restrict__ src, i64 n_words, const __grid_constant__ PeerPtrs P,
+              const __grid_constant__ PeerSync S, i64 dst_offset_words)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (int p = 0; p < S.world; p++) {
+        double* dst = P.out[p] + dst_offset_words;
+        for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) dst[i] = __ldg(src + i);
+    }
+    peer_finish(S);
+}
+
+static int fill_sync(PeerSync& S, uint64_t* const* peer_flags_host, int rank, int world, uint64_t epoch,
+                     uint32_t* done_counter, uint64_t* err_flag)
+{
+    if (!peer_flags_host || !done_counter || !err_flag || world < 1 || world > PEER_MAX || rank < 0 || rank >= world)
+        return fgk_fail(FGK_ERR_ARG, "fgk_peer: bad synchronisation argument");
+    for (int p = 0; p < PEER_MAX; p++) S.f[p] = p < world ? (unsigned long long*)peer_flags_host[p] : nullptr;
+    S.done = done_counter;
+    S.err = (unsigned long long*)err_flag;
+    S.epoch = epoch;
+    S.rank = rank;
+    S.world = world;
+    return FGK_OK;
+}
+
+extern "C" int fgk_peer_step(int64_t n_rows, const int64_t* slice_ptr, const void* cols_or_packed,
+                             const double* vals, const double* diag, const double* x,
+                             double* const* peer_out_host, int flags, int64_t row_offset,
+                             uint64_t* const* peer_flags_host, int rank, int world, uint64_t epoch,
+                             uint32_t* done_counter, uint64_t* err_flag, int device, void* stream)
+{
+    const bool cplx = (flags & FGK_PEER_COMPLEX) != 0, packed = (flags & FGK_PEER_PACKED_F32) != 0;
+    if (n_rows <= 0) return fgk_fail(FGK_ERR_ARG, "fgk_peer_step: every rank needs at least one row");
+    if (!slice_ptr || !cols_or_packed || !x || !peer_out_host || (packed ? !diag : !vals))
+        return fgk_fail(FGK_ERR_ARG, "fgk_peer_step: bad argument");
+    PeerSync S;
+    int rc = fill_sync(S, peer_flags_host, rank, world, epoch, done_counter, err_flag);
+    if (rc != FGK_OK) return rc;
+    FGK_CUDA(cudaSetDevice(device));
+    PeerPtrs P;
+    for (int p = 0; p < PEER_MAX; p++) P.out[p] = p < world ? peer_out_host[p] : nullptr;
+    const unsigned grid = (unsigned)((n_rows + 31) / 32);
+    cudaStream_t st = (cudaStream_t)stream;
+#define FGK_STEP(C, K)                                                                               \
+    k_peer_step<C, K, 4><<<grid, 128, 0, st>>>(n_rows, (const i64*)slice_ptr, cols_or_packed, vals, diag, x, P, S, row_offset)
+    if (cplx && packed) FGK_STEP(true, true);
+    else if (cplx) FGK_STEP(true, false);
+    else if (packed) FGK_STEP(false, true);
+    else FGK_STEP(false, false);
+#undef FGK_STEP
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
+extern "C" int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* const* peer_dst_host,
+                               int64_t dst_offset_bytes, uint64_t* const* peer_flags_host, int rank, int world,
+                               uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag, int device, void* stream)
+{
+    if (!src_local || !peer_dst_host || n_bytes < 0 || (n_bytes & 7) || (dst_offset_bytes & 7) ||
+        ((uintptr_t)src_local & 7))
+        return fgk_fail(FGK_ERR_ARG, "fgk_peer_gather: pointers, size and offset must be 8-byte multiples");
+    PeerSync S;
+    int rc = fill_sync(S, peer_flags_host, rank, world, epoch, done_counter, err_flag);
+    if (rc != FGK_OK) return rc;
+    FGK_CUDA(cudaSetDevice(device));
+    PeerPtrs P;
+    for (int p = 0; p < PEER_MAX; p++) P.out[p] = p < world ? (double*)peer_dst_host[p] : nullptr;
+    const i64 words = n_bytes / 8;
+    i64 need = (words + 255) / 256, cap = (i64)fgk_sm_count(device) * 4;
+    if (need < 1) need = 1;
+    k_peer_gather<<<(unsigned)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        (const double*)src_local, words, P, S, dst_offset_bytes / 8);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}
+
 extern "C" int fgk_spmv_sell_f64_allgather(int64_t n_rows, const int64_t* slice_ptr,
                                            const int32_t* sell_cols, const double* sell_vals,
                                            const double* x, double* const* peer_out_host, int world,

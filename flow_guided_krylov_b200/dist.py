@@ -246,23 +246,39 @@ class _DevArray:
 
 
 class FusedShardedOperator:
-    """Row-block sharded H with y = H x produced directly in every rank's next vector
-    buffer: fgk_spmv_sell_f64_allgather stores each y_r into the peer-mapped buffers of all
-    ranks while it streams the matrix, and fgk_peer_barrier closes the step -- no separate
-    collective.  Buffers ping-pong.  Real FP64 vectors (the Davidson / power-iteration side
-    of Stage 4); complex vectors use ShardedOperator."""
+    """Row-block sharded H whose product, all-gather and barrier are ONE kernel launch:
+    fgk_peer_step stores each y_r straight into every rank's next-vector buffer (peer-mapped
+    memory over NVLink) while it streams the matrix, and its last CTA closes the step with a flag
+    barrier.  Buffers ping-pong.  Real FP64 and complex128 vectors; FP64 SELL-32 storage or, when
+    the operator has it, the packed exact-float32 SELL-32 storage (8 B/nnz).
 
-    def __init__(self, P, group=None):
+    gather_local / matvec_local serve ROW-SHARDED Krylov vectors (solvers.lowest_eigenpairs with
+    a sharded operator): the rank's slice of x is distributed by peer stores (fgk_peer_gather) and
+    only the local rows of y are produced -- nothing full-length is computed twice.
+    matvec_host uploads only this rank's slice of a host vector."""
+
+    ERR_POLL = 64          # steps between looks at the barrier's error flag
+
+    def __init__(self, P, group=None, storage="auto"):
         import ctypes as C
         from . import _native as nat
-        self.P = P.to_sell()
+        if storage not in ("auto", "sell", "packed"):
+            raise ValueError("storage must be 'auto', 'sell' or 'packed'")
+        if storage == "packed":
+            P.to_sell_packed()
+        if storage == "sell" or (storage == "auto" and getattr(P, "_sellf", None) is None):
+            P.to_sell()
+        self.packed = storage == "packed" or (storage == "auto" and getattr(P, "_sellf", None) is not None)
+        self.P = P
         self.n = P.n
         self.rank, self.world = world()
         self.dev = nat.device_index(P.device)
         self.device = P.device
         self.row_begin, self.row_end = P.row_begin, P.row_end
+        if P.n_rows < 1:
+            raise ValueError("FusedShardedOperator: every rank needs at least one row")
         L = nat.lib()
-        nbytes = 8 * self.n
+        nbytes = 16 * self.n                    # room for a complex128 vector
         own, handles = [], []
         for _ in range(3):                     # two vector buffers + the flag array
             ptr, h = C.c_void_p(), C.create_string_buffer(64)
@@ -290,10 +306,15 @@ class FusedShardedOperator:
         self._bufs = [VP(*ptrs[0]), VP(*ptrs[1])]
         self._flags = VP(*ptrs[2])
         self._views = [torch.as_tensor(_DevArray(own[b], self.n), device=P.device) for b in range(2)]
+        self._zviews = [torch.as_tensor(_DevArray(own[b], self.n, "<c16"), device=P.device) for b in range(2)]
         self._err = torch.zeros(1, dtype=torch.int64, device=P.device)
+        self._done = torch.zeros(1, dtype=torch.int32, device=P.device)
         self._epoch = 0
         self._cur = 0
+        self._cplx = False
         self._diag = None
+        self._failed = False
+        self._host_io = None
         if self.world > 1:
             dist.barrier(group=group)          # every rank has mapped every buffer
 
@@ -301,48 +322,105 @@ class FusedShardedOperator:
         from . import _native as nat
         L = nat.lib()
         torch.cuda.synchronize()
-        if self.world > 1:
+        if self.world > 1 and not self._failed:     # after a lost peer the others may never arrive
             dist.barrier()
         for q in getattr(self, "_opened", []):
             L.fgk_peer_close(q, self.dev)
         self._opened = []
-        self._views = []
+        self._views, self._zviews = [], []
         for q in getattr(self, "_own", []):
             L.fgk_peer_free(q, self.dev)
         self._own = []
 
     def current(self):
         """the full current vector on this rank (a view: valid until the step after next)."""
-        return self._views[self._cur]
+        return (self._zviews if self._cplx else self._views)[self._cur]
 
     def load(self, x):
-        self._views[self._cur].copy_(x)
+        self._cplx = x.is_complex()
+        self.current().copy_(x)
+
+    def _sync_args(self):
+        from . import _native as nat
+        self._epoch += 1
+        if self._epoch % self.ERR_POLL == 0:
+            self.check()
+        return (self._flags, self.rank, self.world, self._epoch, nat.ptr(self._done), nat.ptr(self._err, torch.int64),
+                self.dev, nat.stream_ptr(self.device))
 
     def step(self):
-        """cur <- H cur on every rank; returns the new current vector (view)."""
+        """cur <- H cur on every rank (one launch); returns the new current vector (view)."""
         import ctypes as C
         from . import _native as nat
         L = nat.lib()
-        st = nat.stream_ptr(self.device)
-        sp, sc, sv = self.P._sell
         nxt = 1 - self._cur
-        nat.check(L.fgk_spmv_sell_f64_allgather(
-            self.P.n_rows, nat.ptr(sp, torch.int64), nat.ptr(sc, torch.int32), nat.ptr(sv, torch.float64),
-            C.c_void_p(self._own[self._cur]), self._bufs[nxt], self.world, self.row_begin, self.dev, st))
-        self._epoch += 1
-        nat.check(L.fgk_peer_barrier(self._flags, self.rank, self.world, self._epoch,
-                                     nat.ptr(self._err, torch.int64), self.dev, st))
+        flags = (nat.PEER_COMPLEX if self._cplx else 0) | (nat.PEER_PACKED_F32 if self.packed else 0)
+        if self.packed:
+            sp, pk, dg = self.P._sellf
+            a_cols, a_vals, a_diag = nat.ptr(pk), None, nat.ptr(dg, torch.float64)
+        else:
+            sp, sc, sv = self.P._sell
+            a_cols, a_vals, a_diag = nat.ptr(sc, torch.int32), nat.ptr(sv, torch.float64), None
+        nat.check(L.fgk_peer_step(
+            self.P.n_rows, nat.ptr(sp, torch.int64), a_cols, a_vals, a_diag, C.c_void_p(self._own[self._cur]),
+            self._bufs[nxt], flags, self.row_begin, *self._sync_args()))
         self._cur = nxt
-        return self._views[nxt]
+        return self.current()
+
+    def gather_local(self, x_local):
+        """distribute this rank's slice (rows row_begin:row_end) of a row-sharded vector into every
+        rank's current buffer; afterwards current() is the full vector everywhere."""
+        import ctypes as C
+        from . import _native as nat
+        self._cplx = x_local.is_complex()
+        x_local = x_local.contiguous()
+        if x_local.shape[0] != self.P.n_rows:
+            raise ValueError("gather_local: expected this rank's row block")
+        w = 16 if self._cplx else 8
+        nat.check(nat.lib().fgk_peer_gather(
+            C.c_void_p(x_local.data_ptr()), w * self.P.n_rows, self._bufs[self._cur], w * self.row_begin,
+            *self._sync_args()))
+        return self.current()
+
+    def matvec_local(self, x_local, out=None):
+        """y[rows of this rank] = (H x)[rows] for a row-sharded x: peer gather of the input + the
+        plain local product (no output broadcast)."""
+        xf = self.gather_local(x_local)
+        y = self.P.matvec(xf, out=out, fmt="packed" if self.packed else "sell")
+        # the next gather overwrites the buffer xf lives in: ping-pong so that a peer that is one
+        # call ahead cannot touch the vector this rank's product is still reading
+        self._cur = 1 - self._cur
+        return y
 
     def check(self):
         e = int(self._err.item())
         if e:
-            raise RuntimeError(f"fgk_peer_barrier: a peer never arrived at epoch {e}")
+            self._failed = True
+            raise RuntimeError(f"fgk_peer barrier: a peer never arrived at epoch {e}")
 
     def matvec(self, x_full):
         self.load(x_full)
         return self.step().clone()
+
+    def matvec_host(self, x_host, out=None):
+        """host-buffer product on N GPUs: this rank uploads ONLY its slice of x (pinned host
+        memory), the slices are exchanged over NVLink (fgk_peer_gather), one fused step runs, and
+        the rank's rows of y come back in a pinned host tensor."""
+        if not torch.is_tensor(x_host):
+            x_host = torch.from_numpy(x_host)
+        key = x_host.dtype
+        if self._host_io is None or self._host_io[0] != key:
+            ydt = torch.complex128 if x_host.is_complex() else torch.float64
+            self._host_io = (key, torch.empty(self.P.n_rows, dtype=ydt, device=self.device),
+                             torch.empty(self.P.n_rows, dtype=ydt).pin_memory())
+        _, xl, yh = self._host_io
+        xl.copy_(x_host[self.row_begin:self.row_end], non_blocking=True)
+        self.gather_local(xl)
+        ynew = self.step()
+        dst = out if out is not None else yh
+        dst.copy_(ynew[self.row_begin:self.row_end], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return dst
 
     def diagonal(self):
         if self._diag is None:

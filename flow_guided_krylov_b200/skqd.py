@@ -5,6 +5,18 @@ Host-side mirror of reference src/krylov/skqd.py for MOLECULAR Hamiltonians:
   branches only), FlowGuidedSKQD (:891-1059) -- same constructor / method
   signatures and the same result dictionaries.
 
+Two subspace modes (SKQDConfig.subspace_mode):
+  * "full"     -- the reference's construction: every particle-conserving determinant
+                  (C(n,na) C(n,nb) of them, :135-177); exact, feasible up to a few million;
+  * "adaptive" -- SURVEY 8(f) rank 3, for spaces the reference cannot enumerate (32 orbitals:
+                  1.1e14): |psi_k> lives on a GROWING determinant set.  Before every time step the
+                  set is extended by the connections x of its most populated members j, ranked by
+                  the first-order amplitude they receive, max_j |<x|H|j> psi_j| (the PT2 engine in
+                  MAXABS mode), up to a budget; H is rebuilt on the new set by the row builders
+                  and exp(-i dt H_S) acts inside it.  When the set is closed under H (small
+                  molecules with a generous budget) this IS the full-space evolution.
+  "auto" picks full up to SKQDConfig.full_subspace_limit determinants.
+
 What changed underneath:
   * the particle-conserving subspace is a packed determinant array + device hash
     index instead of a Python list + tuple dict (:135-177);
@@ -54,6 +66,19 @@ class SKQDConfig:
     # eigsh(k=2,'SA',return_eigenvectors=False)[0] is lambda_1 for n >= 100); only the
     # golden-parity tests switch it on.
     reference_compat: bool = False
+    # ---- engine knobs of the sampled-subspace ("adaptive") evolution; the reference's own
+    # SKQDConfig has none of them and gets the defaults ----
+    subspace_mode: str = "auto"            # "auto" | "full" | "adaptive"
+    full_subspace_limit: int = 2_000_000   # auto: enumerate the full space up to this many determinants
+    max_subspace_size: int = 1 << 20       # adaptive: cap of the evolving determinant set
+    expand_sources: int = 512              # adaptive: members (largest amplitude) whose connections may enter per round
+    expand_new_per_round: int = 262_144    # adaptive: determinants added per growth round at most
+    expand_rounds: int = 1                 # adaptive: growth rounds before every time step
+
+
+def _cfg(config, name):
+    """engine knob with its default (the unchanged pipeline passes the REFERENCE's SKQDConfig)"""
+    return getattr(config, name, getattr(SKQDConfig, name))
 
 
 class SampleBasedKrylovDiagonalization:
@@ -74,8 +99,19 @@ class SampleBasedKrylovDiagonalization:
         self._subspace_dets = None
         self._subspace_index = None
         self._subspace_H = None
-        self._setup_particle_conserving_subspace()
+        self._subspace_op = None
         self.initial_state = initial_state if initial_state is not None else hamiltonian.get_hf_state()
+        H = hamiltonian
+        n_valid = comb(H.n_orbitals, H.n_alpha) * comb(H.n_orbitals, H.n_beta)
+        mode = _cfg(self.config, "subspace_mode")
+        if mode not in ("auto", "full", "adaptive"):
+            raise ValueError(f"subspace_mode must be 'auto', 'full' or 'adaptive', got {mode!r}")
+        self.adaptive = mode == "adaptive" or (mode == "auto" and n_valid > _cfg(self.config, "full_subspace_limit"))
+        self.subspace_history: List[int] = []      # adaptive: size of the set at every time step
+        if self.adaptive:
+            self._setup_adaptive_subspace()
+        else:
+            self._setup_particle_conserving_subspace()
         if self.config.total_evolution_time is not None:                     # :123-128
             self.time_step = self.config.total_evolution_time / self.config.num_trotter_steps
         else:
@@ -101,6 +137,64 @@ class SampleBasedKrylovDiagonalization:
         self._subspace_dets = H.fci_dets()
         self._subspace_index = BasisIndex(self._subspace_dets)
 
+    # ---- adaptive mode: the evolving determinant set ------------------------------------------
+    def _seed_dets(self):
+        """determinants the evolving set starts from (FlowGuidedSKQD adds the NF basis)"""
+        return self.hamiltonian.pack(self.initial_state.to(self.device))
+
+    def _setup_adaptive_subspace(self):
+        self._set_subspace(sort_unique_dets(self._seed_dets(), self.hamiltonian.n_orbitals))
+
+    def _set_subspace(self, dets):
+        self._subspace_dets = dets.contiguous()
+        self._subspace_index = BasisIndex(self._subspace_dets)
+        self._subspace_H = None
+        self._subspace_op = None
+        if hasattr(self, "_expm_cache"):
+            del self._expm_cache
+
+    @staticmethod
+    def _world():
+        import torch.distributed as tdist
+        return tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
+
+    def _grow_subspace(self, psi: torch.Tensor) -> torch.Tensor:
+        """One or more growth rounds (see the module docstring); returns psi embedded in the new set."""
+        from .expansion import pt2_select
+        H, cfg = self.hamiltonian, self.config
+        cap = int(_cfg(cfg, "max_subspace_size"))
+        amp = psi.abs()
+        for _ in range(int(_cfg(cfg, "expand_rounds"))):
+            m = self._subspace_dets.shape[0]
+            budget = min(cap - m, int(_cfg(cfg, "expand_new_per_round")))
+            if budget <= 0:
+                break
+            ns = min(int(_cfg(cfg, "expand_sources")), m)
+            coeff = torch.zeros(m, dtype=torch.float64, device=self.device)
+            top = torch.topk(amp, ns).indices if ns < m else torch.arange(m, device=self.device)
+            coeff[top] = amp[top]
+            if self._world() > 1:
+                from . import dist as fdist
+                sel, score, _ = fdist.pt2_select_sharded(H, self._subspace_index, coeff, 0.0, budget,
+                                                         mode=nat.PT2_MAXABS, coeff_cut=0.0)
+            else:
+                sel, score, _ = pt2_select(H, self._subspace_index, coeff, 0.0, budget,
+                                           mode=nat.PT2_MAXABS, coeff_cut=0.0)
+            if sel.shape[0] == 0:
+                break                                   # the set is closed under H (for these sources)
+            old = self._subspace_dets
+            new = sort_unique_dets(torch.cat([old, sel], dim=0), H.n_orbitals)
+            self._set_subspace(new)
+            pos_old = self._subspace_index.lookup(old).long()
+            pos_new = self._subspace_index.lookup(sel).long()
+            psi2 = torch.zeros(new.shape[0], dtype=psi.dtype, device=self.device)
+            psi2[pos_old] = psi
+            amp2 = torch.zeros(new.shape[0], dtype=torch.float64, device=self.device)
+            amp2[pos_old] = amp
+            amp2[pos_new] = self.time_step * score      # first-order amplitude a new member will receive
+            psi, amp = psi2, amp2
+        return psi
+
     @property
     def _subspace_basis(self):
         """(N_fci, num_sites) int64 configurations (compat with skqd.py:169)."""
@@ -109,8 +203,13 @@ class SampleBasedKrylovDiagonalization:
     # :374-419
     def _build_subspace_hamiltonian(self):
         if self._subspace_H is None:
-            self._subspace_H = self.hamiltonian.projected_csr(
-                self._subspace_dets, nat.H_RAW, index=self._subspace_index, packed=True)
+            if self.adaptive and self._world() > 1:     # rows sharded over the ranks
+                from . import dist as fdist
+                self._subspace_H, self._subspace_op = fdist.build_sharded_h(
+                    self.hamiltonian, self._subspace_dets, nat.H_RAW, index=self._subspace_index)
+            else:
+                self._subspace_H = self.hamiltonian.projected_csr(
+                    self._subspace_dets, nat.H_RAW, index=self._subspace_index, packed=True)
             self._subspace_H.optimize_for_matvec()      # ~30 complex H.v per time step
         return self._subspace_H
 
@@ -120,15 +219,21 @@ class SampleBasedKrylovDiagonalization:
     # :275-296 (in the subspace; one step = one expm_multiply)
     def _evolve_subspace(self, psi: torch.Tensor, num_steps: int = 1) -> torch.Tensor:
         P = self._build_subspace_hamiltonian()
+        op = self._subspace_op
         if not hasattr(self, "_expm_cache"):
             from .solvers import one_norm
-            d = P.diagonal()
+            d = P.diagonal() if op is None else op.diagonal()
             mu = float(d.sum()) / P.n
-            cs = one_norm(P) - d.abs() + (d - mu).abs()
+            cs = one_norm(P)
+            if op is not None:                          # column sums of the other ranks' row blocks
+                import torch.distributed as tdist
+                tdist.all_reduce(cs)
+            cs = cs - d.abs() + (d - mu).abs()
             self._expm_cache = (mu, float(cs.max()))
         mu, nrm = self._expm_cache
         for _ in range(num_steps):
-            psi = expm_multiply(P, psi, -1j * self.time_step, mu=mu, norm1=nrm)
+            psi = expm_multiply(P, psi, -1j * self.time_step, mu=mu, norm1=nrm,
+                                matvec=None if op is None else op.matvec)
         return psi
 
     def _subspace_position(self, config: torch.Tensor) -> int:
@@ -144,8 +249,11 @@ class SampleBasedKrylovDiagonalization:
         # inverse-CDF sampling (torch.multinomial refuses more than 2^24 categories, and the
         # subspace may hold up to MAX_SUBSPACE determinants)
         cdf = torch.cumsum(probs, 0)
-        u = torch.rand(num_samples, dtype=cdf.dtype, device=cdf.device) * cdf[-1]
-        idx = torch.searchsorted(cdf, u, right=True).clamp_(max=cdf.shape[0] - 1)
+        u = torch.rand(num_samples, dtype=cdf.dtype, device=cdf.device)
+        if self._world() > 1:                           # every rank must draw the same samples
+            import torch.distributed as tdist
+            tdist.broadcast(u, 0)
+        idx = torch.searchsorted(cdf, u * cdf[-1], right=True).clamp_(max=cdf.shape[0] - 1)
         uniq, counts = torch.unique(idx, return_counts=True)
         dets = self._subspace_dets[uniq]
         # ascending Hilbert index == ascending key (np.unique order of the reference, :563)
@@ -162,6 +270,9 @@ class SampleBasedKrylovDiagonalization:
         if max_krylov_dim is None:
             max_krylov_dim = self.config.max_krylov_dim
         self.krylov_samples, self.krylov_sample_dets, self.krylov_states = [], [], []
+        if self.adaptive:                               # a fresh run starts from the seed set again
+            self._setup_adaptive_subspace()
+        self.subspace_history = []
         n = self._subspace_dets.shape[0]
         psi = torch.zeros(n, dtype=torch.complex128, device=self.device)
         psi[self._subspace_position(self.initial_state)] = 1.0
@@ -173,7 +284,10 @@ class SampleBasedKrylovDiagonalization:
             self.krylov_sample_dets.append(dets)
             self.krylov_samples.append(dict(zip(self._dets_to_bitstrings(dets), counts.tolist())))
             self.krylov_states.append(psi)
+            self.subspace_history.append(int(self._subspace_dets.shape[0]))
             if k < max_krylov_dim - 1:
+                if self.adaptive:
+                    psi = self._grow_subspace(psi)
                 psi = self._evolve_subspace(psi, 1)
         return self.krylov_samples
 
@@ -270,8 +384,15 @@ class FlowGuidedSKQD(SampleBasedKrylovDiagonalization):
 
     def __init__(self, hamiltonian, nf_basis: torch.Tensor, config: Optional[SKQDConfig] = None,
                  initial_state: Optional[torch.Tensor] = None):
+        self.nf_basis = nf_basis            # before super().__init__: the adaptive seed set uses it
         super().__init__(hamiltonian, config, initial_state)
-        self.nf_basis = nf_basis
+
+    def _seed_dets(self):
+        H = self.hamiltonian
+        seed = H.pack(self.initial_state.to(self.device))
+        if self.nf_basis is not None and len(self.nf_basis):
+            seed = torch.cat([seed, H.pack(self.nf_basis.to(self.device))], dim=0)
+        return seed
 
     def _combined_dets(self, krylov_index: int, include_nf: bool = True):
         kd = self._basis_dets(krylov_index, True)

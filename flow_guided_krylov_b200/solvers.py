@@ -43,7 +43,7 @@ class _Phases:
 
 
 def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=None,
-                      diagonal=None, dense_max=DENSE_EIG_MAX, v0=None, phases=None):
+                      diagonal=None, dense_max=DENSE_EIG_MAX, v0=None, phases=None, sharded=None):
     """k lowest eigenpairs of the symmetric operator P (a ProjectedH built with
     H_SYM, or any object with .n plus `matvec`/`diagonal` callables).
     Returns (w (k,) float64 tensor ascending, V (n,k)).
@@ -52,8 +52,13 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
     preconditioner and THICK restart (the lowest Ritz vectors are kept, H V is rotated
     along, no extra products); the small projected matrix lives on the host (numpy eigh),
     so an iteration costs the H.v products plus a handful of n x m device GEMVs and one
-    scalar read-back."""
+    scalar read-back.
+
+    sharded = a dist.FusedShardedOperator: the ROW-SHARDED form of the same iteration (see
+    _davidson_sharded) -- every rank keeps only its row block of the basis vectors."""
     import numpy as np
+    if sharded is not None:
+        return _davidson_sharded(sharded, min(k, P.n), tol, max_iter, max_space, v0, phases)
     n = P.n
     mv = matvec if matvec is not None else (lambda x: _full_matvec(P, x))
     k = min(k, n)
@@ -138,6 +143,108 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         m += added
         ph.mark("project")
     return w_out.clone(), X.T.contiguous()
+
+
+def _davidson_sharded(op, k, tol, max_iter, max_space, v0, phases):
+    """Block Davidson with ROW-SHARDED vectors over a dist.FusedShardedOperator: rank r keeps rows
+    [row_begin, row_end) of every basis vector V_j and of H V_j; a product gathers the new vector
+    over peer memory (fgk_peer_gather) and multiplies the local row block; dot products are summed
+    with one small all-reduce each.  The replicated form repeated all full-length algebra on
+    every rank (0.30 parallel efficiency at 8 GPUs); here only O(m) numbers per
+    iteration are replicated.  Same iteration as lowest_eigenpairs (same start vectors, same
+    restart rule), so the Ritz values agree with it to rounding.  Returns (w, X) with X full-length
+    (all-gathered) on every rank."""
+    import numpy as np
+    import torch.distributed as tdist
+    from .dist import allgather_vector
+    n, lo, hi = op.n, op.row_begin, op.row_end
+    nl = hi - lo
+    diag_full = op.diagonal()
+    diag = diag_full[lo:hi]
+    dev = diag.device
+    ph = _Phases(phases, dev)
+    ph.mark(None)
+    multi = op.world > 1
+
+    def allsum(t):
+        if multi:
+            tdist.all_reduce(t)
+        return t
+
+    nb = min(max(2 * k, k + 2), n)
+    m_max = min(n, max_space if max_space is not None else max(12 * k, 36))
+    m_max = max(m_max, nb + k)
+    keep = min(max(2 * k + 2, m_max // 3), m_max - k)
+    V = torch.zeros(m_max, nl, dtype=torch.float64, device=dev)
+    W = torch.zeros(m_max, nl, dtype=torch.float64, device=dev)
+    start = torch.argsort(diag_full)[:nb]
+    V0 = torch.zeros(n, nb, dtype=torch.float64, device=dev)
+    V0[start, torch.arange(nb, device=dev)] = 1.0
+    gen = torch.Generator(device=dev).manual_seed(20240229)       # same stream on every rank
+    V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen, device=dev)
+    if v0 is not None:
+        V0[:, 0] = v0.to(dev, torch.float64)
+    V0 = V0[lo:hi].contiguous()
+    for _ in range(2):                                   # CholQR2 on the sharded block
+        G = allsum(V0.T @ V0)
+        R = torch.linalg.cholesky(G, upper=True)
+        V0 = torch.linalg.solve_triangular(R, V0, upper=True, left=False)
+    m = nb
+    V[:m] = V0.T
+    del V0
+    for i in range(m):
+        op.matvec_local(V[i], out=W[i])
+    T = np.zeros((m_max, m_max))
+    T[:m, :m] = allsum(V[:m] @ W[:m].T).cpu().numpy()
+    w_out = X = None
+    ph.mark("setup")
+    for _ in range(max_iter):
+        Tm = 0.5 * (T[:m, :m] + T[:m, :m].T)
+        th, s = np.linalg.eigh(Tm)
+        s_dev = torch.from_numpy(np.ascontiguousarray(s.T)).to(dev)
+        thk = torch.from_numpy(th[:k].copy()).to(dev)
+        X = s_dev[:k] @ V[:m]
+        R = s_dev[:k] @ W[:m] - thk[:, None] * X
+        rn = torch.sqrt(allsum((R * R).sum(dim=1))).cpu().numpy()
+        ph.mark("ritz_residual")
+        w_out = thk
+        scale = max(1.0, float(np.abs(th[:k]).max()))
+        if rn.max() < tol * scale:
+            break
+        todo = [i for i in range(k) if rn[i] >= tol * scale]
+        if m + len(todo) > m_max:
+            q = keep
+            V[:q] = s_dev[:q] @ V[:m]
+            W[:q] = s_dev[:q] @ W[:m]
+            T[:] = 0.0
+            T[np.arange(q), np.arange(q)] = th[:q]
+            m = q
+        added = 0
+        for i in todo:
+            den = thk[i] - diag
+            den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
+            t = R[i] / den
+            for _ in range(2):                           # CGS2, coefficients summed over the ranks
+                c = allsum(V[:m + added] @ t)
+                t = t - c @ V[:m + added]
+            nt = float(torch.sqrt(allsum((t * t).sum().reshape(1)))[0])
+            if nt > 1e-10:
+                V[m + added] = t / nt
+                added += 1
+        ph.mark("correction_orth")
+        if added == 0:
+            break
+        for j in range(m, m + added):
+            op.matvec_local(V[j], out=W[j])
+        ph.mark("matvec")
+        blk = allsum(V[:m + added] @ W[m:m + added].T).cpu().numpy()
+        T[:m + added, m:m + added] = blk
+        T[m:m + added, :m + added] = blk.T
+        m += added
+        ph.mark("project")
+    op.check()
+    Xf = torch.stack([allgather_vector(X[i].contiguous(), n) for i in range(X.shape[0])], dim=1)
+    return w_out.clone(), Xf.contiguous()
 
 
 # Al-Mohy & Higham 2011, table 3.1 (tol = 2^-53): theta_m for selected m

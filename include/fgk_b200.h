@@ -204,6 +204,29 @@ int fgk_spmv_sell_f64_allgather(int64_t n_rows, const int64_t* slice_ptr, const 
 int fgk_peer_barrier(uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
                      uint64_t* err_flag, int device, void* stream);
 
+/* One-launch multi-GPU step: product + broadcast + barrier (no reference counterpart).
+ * y = H[row block] x with the rank's rows in SELL-32 storage -- FP64 (cols_or_packed = int32
+ * columns, vals) or packed exact-float32 (cols_or_packed = the uint4 array of fgk_sell_pack_f32,
+ * diag; flag FGK_PEER_PACKED_F32) -- for a real or complex (FGK_PEER_COMPLEX, interleaved) x.
+ * Every y_r is stored into peer_out[p][row_offset + r] on every rank p; the CTA that finishes
+ * last arrives on every rank's flag array (peer_flags as for fgk_peer_barrier) with `epoch` and
+ * waits for all peers: when the kernel completes the output vector is complete on this rank and
+ * every peer has finished reading x.  done_counter: device uint32, zero before the first call.
+ * Every rank must own at least one row.  x must not alias the outputs (ping-pong buffers). */
+#define FGK_PEER_COMPLEX 1
+#define FGK_PEER_PACKED_F32 2
+int fgk_peer_step(int64_t n_rows, const int64_t* slice_ptr, const void* cols_or_packed,
+                  const double* vals, const double* diag, const double* x, double* const* peer_out,
+                  int flags, int64_t row_offset, uint64_t* const* peer_flags, int rank, int world,
+                  uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
+/* All-gather of a row-sharded vector over peer memory: src_local[0 .. n_bytes) goes to
+ * peer_dst[p] + dst_offset_bytes on every rank p (8-byte multiples), closed by the same
+ * barrier.  Distributes the INPUT of a product: row-sharded Krylov vectors, host vectors
+ * uploaded as N slices. */
+int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* const* peer_dst, int64_t dst_offset_bytes,
+                    uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
+                    uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
+
 /* ---- K7/K8 PT2 residual expansion --------------------------------------------------------
  * replaces SelectedCIExpander._find_important_configs (residual_expansion.py:451-554)
  * and ResidualBasedExpander._find_residual_configs (:174-253).

@@ -496,6 +496,84 @@ def test_skqd_real_molecules_vs_reference(fgk, name):
         assert abs(res["energies_krylov"][k - 1] - O.ground_state_energy(g[f"krylov_basis_{k}"], False)[0]) < TOL
 
 
+@pytest.mark.parametrize("name", ["lih", "beh2_sto3g"])
+def test_skqd_adaptive_subspace_equals_full_space_when_closed(fgk, name):
+    """SURVEY 8(f) rank 3 (sampled-subspace SKQD, replaces skqd.py:135-177,298-321,608-614).  With a
+    budget that lets the evolving set close under H, the adaptive evolution IS the full-space one:
+    amplitudes equal the full-mode engine's (1e-12) and the reference's psi_k (float32-diagonal
+    envelope); determinants the set never reaches carry no amplitude in the reference either."""
+    g = load_golden("skqd_" + name)
+    H, O, n_orb = make_pair(fgk, g)
+    kdim = 4
+    full = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(
+        max_krylov_dim=kdim, shots_per_krylov=2000, subspace_mode="full"))
+    ada = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"][:1]), fgk.SKQDConfig(
+        max_krylov_dim=kdim, shots_per_krylov=2000, subspace_mode="adaptive",
+        max_subspace_size=1 << 20, expand_sources=1 << 20, expand_new_per_round=1 << 20, expand_rounds=6))
+    assert ada.adaptive and not full.adaptive
+    torch.manual_seed(0)
+    full.generate_krylov_samples(progress=False)
+    torch.manual_seed(0)
+    ada.generate_krylov_samples(progress=False)
+    assert ada.subspace_history[0] <= 2 and ada.subspace_history[-1] <= len(g["subspace"])
+    sub = ada._subspace_dets                                # final (closed) set, ascending key
+    pos = full._subspace_index.lookup(sub).long()
+    assert bool((pos >= 0).all())
+    outside = torch.ones(len(g["subspace"]), dtype=torch.bool, device="cuda:0")
+    outside[pos] = False
+    for k in range(kdim):
+        pf = full.krylov_states[k]
+        pa = ada.krylov_states[k]
+        # embed the adaptive state (on ITS set at step k) into the full space
+        emb = torch.zeros_like(pf)
+        if pa.shape[0] == sub.shape[0]:
+            emb[pos] = pa
+        else:                                               # step 0: still the seed set
+            emb[full._subspace_position(H.get_hf_state())] = 1.0
+        assert float((emb - pf).abs().max()) < 1e-12
+        if bool(outside.any()):
+            assert float(pf[outside].abs().max()) < 1e-14
+        if k >= 1:
+            assert np.abs(emb.cpu().numpy() - g["psi_steps"][k - 1]).max() < 2e-5
+    # run_with_nf in adaptive mode: variational, improves on (or equals) the NF-only energy
+    torch.manual_seed(1)
+    res = ada.run_with_nf(progress=False)
+    E_fci, _ = O.diagonalize(O.fci_basis())
+    assert res["best_stable_energy"] <= res["energy_nf_only"] + 1e-12
+    assert res["best_stable_energy"] >= E_fci - 1e-6
+
+
+def test_skqd_adaptive_subspace_32_orbitals(fgk):
+    """configs[3] shape: 32 orbitals / 8+8 electrons, FCI dimension 1.1e14 -- the reference cannot
+    even enumerate the space (skqd.py:135-177); the adaptive evolution runs on a capped set."""
+    from bench import synth_integrals, cas_window_basis
+    h1, gg = synth_integrals(32, seed=0)
+    H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, 16, 32, 8, 8), "cuda:0")
+    cas = cas_window_basis(32, 4, 14, 4)
+    rng = np.random.default_rng(0)
+    nf = torch.from_numpy(cas[rng.choice(len(cas), 400, replace=False)].view(np.int64)).cuda()
+    nf_cfg = H.unpack(nf)
+    cfg = fgk.SKQDConfig(max_krylov_dim=3, shots_per_krylov=5000, max_subspace_size=60000,
+                         expand_sources=64, expand_new_per_round=30000)
+    sk = fgk.FlowGuidedSKQD(H, nf_cfg, cfg)
+    assert sk.adaptive                                       # auto: 1.1e14 > full_subspace_limit
+    torch.manual_seed(0)
+    res = sk.run_with_nf(progress=False)
+    hist = sk.subspace_history
+    assert hist[0] == 401 and hist == sorted(hist) and hist[-1] <= 60000 and hist[-1] > hist[0]
+    for k, psi in enumerate(sk.krylov_states):
+        nrm = float(torch.linalg.norm(psi))
+        assert abs(nrm - 1.0) < 0.2                          # raw directed H (F3): not exactly unitary
+    assert len(res["energies_combined"]) == 2
+    assert res["best_stable_energy"] <= res["energy_nf_only"] + 1e-12
+    assert res["basis_sizes_combined"][-1] >= 401
+    # every sampled determinant has the right particle numbers and lies in the evolving set
+    last = sk.krylov_sample_dets[-1]
+    assert bool((sk._subspace_index.lookup(last) >= 0).all())
+    with pytest.raises(ValueError):
+        fgk.FlowGuidedSKQD(H, nf_cfg, fgk.SKQDConfig(subspace_mode="full"))
+
+
 def test_skqd_ground_state_energy_modes(fgk):
     g = load_golden("skqd_lih")
     H, O, _ = make_pair(fgk, g)
