@@ -41,6 +41,12 @@ _SIGNATURES = {
     "fgk_projh_fill": (ci, [vp, vp, i64, i64, ci, vp, vp, vp, vp]),
     "fgk_projh_fill_sell": (ci, [vp, vp, i64, i64, ci, vp, vp, vp, vp]),
     "fgk_csr_sort_rows": (ci, [i64, vp, vp, vp, ci, vp]),
+    "fgk_strlists_create": (ci, [vp, vp, vp, C.POINTER(vp)]),
+    "fgk_strlists_destroy": (ci, [vp]),
+    "fgk_strlists_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+    "fgk_projh_packed_bound": (ci, [vp, vp, vp, i64, i64, vp, vp]),
+    "fgk_projh_packed_count": (ci, [vp, vp, vp, i64, i64, ci, i64, vp, vp]),
+    "fgk_projh_packed_fill": (ci, [vp, vp, vp, i64, i64, ci, vp, vp, vp, vp, vp]),
     "fgk_spmv_f64": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_z": (ci, [i64, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_sell_fill": (ci, [i64, vp, vp, vp, vp, vp, vp, ci, vp]),

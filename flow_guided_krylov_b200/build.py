@@ -9,8 +9,8 @@ import subprocess
 import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["fgk_ham.cu", "fgk_index.cu", "fgk_projh.cu", "fgk_spmv.cu", "fgk_pt2.cu", "fgk_peer.cu"]
-HEADERS = ["fgk_core.cuh", "fgk_internal.cuh", "fgk_tables.h", os.path.join("..", "..", "include", "fgk_b200.h")]
+SOURCES = ["fgk_ham.cu", "fgk_index.cu", "fgk_projh.cu", "fgk_projh4.cu", "fgk_spmv.cu", "fgk_pt2.cu", "fgk_peer.cu"]
+HEADERS = ["fgk_core.cuh", "fgk_internal.cuh", "fgk_lists.cuh", "fgk_tables.h", os.path.join("..", "..", "include", "fgk_b200.h")]
 LIB = os.path.join(CSRC, "libfgk_b200.so")
 
 NVCC_FLAGS = [

@@ -8,6 +8,7 @@
 #include <utility>
 #include <vector>
 #include "fgk_core.cuh"
+#include "fgk_lists.cuh"
 #include "fgk_tables.h"
 
 struct HcHam { HostTables T; HamView V; };
@@ -387,6 +388,63 @@ long hc_check_split(void* h, const u64* dets, long n_dets)
             }
     }
     return bad;
+}
+
+// String-driven row (the k_projh4 strategy, fgk_lists.cuh): replacement lists per distinct string
+// with signed values and separable alpha-beta factors, rows assembled from list entries and the
+// (alpha rank, beta rank) pair map in the kernel's order: diagonal, alpha singles, beta singles,
+// alpha doubles, beta doubles, alpha-beta (beta single outside, alpha single inside).
+long hc_bra_row4(void* h, const u64* basis, long n, long i, int mode, int* out_cols, double* out_vals, long cap)
+{
+    HcHam* H = (HcHam*)h;
+    const HamView& V = H->V;
+    std::map<u64, int> arank, brank;
+    for (long k = 0; k < n; k++) { arank[basis[2 * k]] = 0; brank[basis[2 * k + 1]] = 0; }
+    std::vector<u64> alist, blist;
+    for (auto& kv : arank) { kv.second = (int)alist.size(); alist.push_back(kv.first); }
+    for (auto& kv : brank) { kv.second = (int)blist.size(); blist.push_back(kv.first); }
+    std::map<std::pair<int, int>, long> pair;
+    for (long k = 0; k < n; k++) pair[{arank[basis[2 * k]], brank[basis[2 * k + 1]]}] = k;   // last index wins
+    const fgk_det d = {basis[2 * i], basis[2 * i + 1]};
+    const int ia = arank[d.a], ib = brank[d.b];
+    const bool sym = (mode & 1) != 0, drop0 = (mode & 2) != 0;
+    std::vector<LEntry> S[2], D[2];
+    for (int spin = 0; spin < 2; spin++) {
+        const u64 w = spin ? d.b : d.a;
+        const std::vector<u64>& list = spin ? blist : alist;
+        for (int t = 0; t < (int)list.size(); t++) {
+            const int pc = fgk_popc(list[t] ^ w);
+            if (pc == 2) S[spin].push_back(single_entry(V, w, list[t], t, ldf_host));
+            else if (pc == 4) D[spin].push_back(double_entry(V, w, list[t], t, ldf_host));
+        }
+    }
+    long m = 0;
+    if (m < cap) { out_cols[m] = (int)i; out_vals[m] = diag_element(V, d, ldd_host); }
+    m++;
+    auto column = [&](int ra, int rb) -> long {
+        auto it = pair.find({ra, rb});
+        return it == pair.end() ? -1 : it->second;
+    };
+    auto one = [&](float vij, float vji, long j) {
+        double v;
+        if (j >= 0 && entry_value(sym, drop0, vij, vji, v)) {
+            if (m < cap) { out_cols[m] = (int)j; out_vals[m] = v; }
+            m++;
+        }
+    };
+    for (const LEntry& e : S[0]) one(e.vij, e.vji, column(e.rank, ib));
+    for (const LEntry& e : S[1]) one(e.vij, e.vji, column(ia, e.rank));
+    for (const LEntry& e : D[0]) one(e.vij, e.vji, column(e.rank, ib));
+    for (const LEntry& e : D[1]) one(e.vij, e.vji, column(ia, e.rank));
+    for (const LEntry& eb : S[1])
+        for (const LEntry& ea : S[0]) {
+            const long j = column(ea.rank, eb.rank);
+            if (j < 0) continue;
+            float vij, vji;
+            ab_values(V, ea, eb, sym, ldf_host, vij, vji);
+            one(vij, vji, j);
+        }
+    return m;
 }
 
 // the PT2 accumulator arithmetic (fgk_pt2.cu: fx_from_double -> 128-bit integer adds with the

@@ -21,7 +21,7 @@
 // most of the device, so the buffers come from a stream-ordered memory pool OWNED BY THIS
 // LIBRARY (one per device, blocks kept between indices).  The device's default pool -- which
 // belongs to the host application -- is not touched.
-static cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st, int device)
+cudaError_t fgk_pool_alloc(void** p, size_t bytes, cudaStream_t st, int device)
 {
     static cudaMemPool_t pools[64] = {nullptr};
     cudaMemPool_t& pool = pools[device & 63];
@@ -178,7 +178,7 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     void* tmp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // words, sorted, unique a, unique b, cub / counts
     const fgk_det* d = (const fgk_det*)dets;
     u64 tsize = pow2_at_least((u64)(n > 0 ? 2 * n : 1) < 64 ? 64 : (u64)2 * n);
-    FGK_CUDA_I(pool_alloc((void**)&I->table, tsize * sizeof(u64), st, device));
+    FGK_CUDA_I(fgk_pool_alloc((void**)&I->table, tsize * sizeof(u64), st, device));
     FGK_CUDA_I(cudaMemsetAsync(I->table, 0xFF, tsize * sizeof(u64), st));
     unsigned long long h_cnt[2] = {0, 0};
     if (n > 0) {
@@ -190,8 +190,8 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
         cub::DeviceSelect::Unique(nullptr, cub_b, (const u64*)nullptr, (u64*)nullptr, (unsigned long long*)nullptr,
                                   (int)n, st);
         const size_t cub_bytes = ((cub_a > cub_b ? cub_a : cub_b) + 255) & ~(size_t)255;
-        for (int t = 0; t < 4; t++) FGK_CUDA_I(pool_alloc(&tmp[t], (size_t)n * sizeof(u64), st, device));
-        FGK_CUDA_I(pool_alloc(&tmp[4], cub_bytes + 2 * sizeof(unsigned long long), st, device));
+        for (int t = 0; t < 4; t++) FGK_CUDA_I(fgk_pool_alloc(&tmp[t], (size_t)n * sizeof(u64), st, device));
+        FGK_CUDA_I(fgk_pool_alloc(&tmp[4], cub_bytes + 2 * sizeof(unsigned long long), st, device));
         unsigned long long* d_cnt = (unsigned long long*)((char*)tmp[4] + cub_bytes);
         for (int which = 0; which < 2; which++) {
             size_t tb = cub_bytes;
@@ -209,13 +209,13 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
     I->n_beta_strings = (i64)h_cnt[1];
     u64 asz = pow2_at_least(h_cnt[0] * 4 < 64 ? 64 : h_cnt[0] * 4);
     u64 bsz = pow2_at_least(h_cnt[1] * 4 < 64 ? 64 : h_cnt[1] * 4);
-    FGK_CUDA_I(pool_alloc((void**)&I->aset, asz * sizeof(u64), st, device));
-    FGK_CUDA_I(pool_alloc((void**)&I->bset, bsz * sizeof(u64), st, device));
+    FGK_CUDA_I(fgk_pool_alloc((void**)&I->aset, asz * sizeof(u64), st, device));
+    FGK_CUDA_I(fgk_pool_alloc((void**)&I->bset, bsz * sizeof(u64), st, device));
     FGK_CUDA_I(cudaMemsetAsync(I->aset, 0xFF, asz * sizeof(u64), st));
     FGK_CUDA_I(cudaMemsetAsync(I->bset, 0xFF, bsz * sizeof(u64), st));
     // right-sized ascending lists of the distinct strings (scanned by the projected-H builder)
-    FGK_CUDA_I(pool_alloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64), st, device));
-    FGK_CUDA_I(pool_alloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64), st, device));
+    FGK_CUDA_I(fgk_pool_alloc((void**)&I->alist, (h_cnt[0] ? h_cnt[0] : 1) * sizeof(u64), st, device));
+    FGK_CUDA_I(fgk_pool_alloc((void**)&I->blist, (h_cnt[1] ? h_cnt[1] : 1) * sizeof(u64), st, device));
     if (n > 0) {
         FGK_CUDA_I(cudaMemcpyAsync(I->alist, tmp[2], h_cnt[0] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
         FGK_CUDA_I(cudaMemcpyAsync(I->blist, tmp[3], h_cnt[1] * sizeof(u64), cudaMemcpyDeviceToDevice, st));
@@ -226,15 +226,15 @@ extern "C" int fgk_index_create(const uint64_t* dets, int64_t n, int device, voi
         // rank form: string ranks per determinant and, when the basis covers at least 1/16 of its
         // alpha x beta string product (always for CAS-like / product bases), the dense pair table
         // the rank-based projected-H builder reads instead of probing the hash table
-        FGK_CUDA_I(pool_alloc((void**)&I->ra, (size_t)n * sizeof(int32_t), st, device));
-        FGK_CUDA_I(pool_alloc((void**)&I->rb, (size_t)n * sizeof(int32_t), st, device));
+        FGK_CUDA_I(fgk_pool_alloc((void**)&I->ra, (size_t)n * sizeof(int32_t), st, device));
+        FGK_CUDA_I(fgk_pool_alloc((void**)&I->rb, (size_t)n * sizeof(int32_t), st, device));
         k_string_ranks<<<grid1d(n, device), 256, 0, st>>>(d, n, I->alist, I->n_alpha_strings, I->blist,
                                                           I->n_beta_strings, I->ra, I->rb);
         FGK_CUDA_I(cudaGetLastError());
         const i64 prod = I->n_alpha_strings * I->n_beta_strings;
         const i64 lim = 16 * n > (1ll << 20) ? 16 * n : (1ll << 20);
         if (prod <= lim && prod < (1ll << 31)) {
-            FGK_CUDA_I(pool_alloc((void**)&I->pair, (size_t)prod * sizeof(int32_t), st, device));
+            FGK_CUDA_I(fgk_pool_alloc((void**)&I->pair, (size_t)prod * sizeof(int32_t), st, device));
             FGK_CUDA_I(cudaMemsetAsync(I->pair, 0xFF, (size_t)prod * sizeof(int32_t), st));
             k_pair_fill<<<grid1d(n, device), 256, 0, st>>>(I->ra, I->rb, n, I->n_beta_strings, I->pair);
             FGK_CUDA_I(cudaGetLastError());

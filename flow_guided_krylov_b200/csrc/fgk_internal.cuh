@@ -102,6 +102,8 @@ static const int FGK_WARPS_PER_BLOCK = 8;
 static const int FGK_BLOCK = FGK_WARPS_PER_BLOCK * 32;
 
 int fgk_sm_count(int device);
+// stream-ordered allocation from the library's own memory pool (fgk_index.cu); free with cudaFreeAsync
+cudaError_t fgk_pool_alloc(void** p, size_t bytes, cudaStream_t st, int device);
 
 // ---- device helpers ---------------------------------------------------------------
 #if defined(__CUDACC__)

@@ -154,14 +154,21 @@ def allreduce_scalar(x: float, op="sum", device="cpu") -> float:
 
 
 # ---- engine-facing helpers (CUDA) ----------------------------------------------------------
-def build_sharded_h(ham, dets, mode, index=None, sort_rows=False):
-    """each rank builds CSR rows of its block; returns (ProjectedH block, ShardedOperator)."""
+def build_sharded_h(ham, dets, mode, index=None, sort_rows=False, operator=False):
+    """each rank builds the rows of its block; returns (ProjectedH block, ShardedOperator).
+    operator=False: CSR rows (reference-comparable form); operator=True: the best storage for
+    repeated H.v (ham.projected_operator: packed SELL-32 built directly when possible)."""
     from .hamiltonian import BasisIndex
     rank, ws = world()
     idx = index if index is not None else BasisIndex(dets)
     lo, hi = row_block(dets.shape[0], rank, ws)
-    P = ham.projected_csr(dets, mode, row_begin=lo, row_end=hi, index=idx, packed=True,
-                          sort_rows=sort_rows)
+    if operator:
+        P = ham.projected_operator(dets, mode, row_begin=lo, row_end=hi, index=idx, packed=True, min_rows=1024)
+        if not getattr(P, "sell_only", False):
+            P.optimize_for_matvec(min_rows=0)
+    else:
+        P = ham.projected_csr(dets, mode, row_begin=lo, row_end=hi, index=idx, packed=True,
+                              sort_rows=sort_rows)
     op = ShardedOperator(dets.shape[0], P.matvec, P.diagonal())
     return P, op
 

@@ -356,15 +356,15 @@ class SelectedCIExpander:
         if self._world() > 1 and n >= self.sharded_min_rows:
             from . import dist as fdist
             index = BasisIndex(dets)
-            Pb, _ = fdist.build_sharded_h(H, dets, nat.H_SYM, index=index)
+            Pb, _ = fdist.build_sharded_h(H, dets, nat.H_SYM, index=index, operator=True)   # packed rows, built directly
             op = fdist.FusedShardedOperator(Pb)
             try:
-                w, v = lowest_eigenpairs(op, k=1, matvec=op.matvec, diagonal=op.diagonal(), dense_max=0)
+                w, v = lowest_eigenpairs(op, k=1, sharded=op)   # row-sharded vectors, peer gather per product
                 op.check()
             finally:
                 op.close()
             return float(w[0]), v[:, 0], index
-        P = H.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)
+        P = H.projected_operator(dets, nat.H_SYM, packed=True)     # CSR below 16,384 rows, packed SELL-32 above
         w, v = lowest_eigenpairs(P, k=1)
         return float(w[0]), v[:, 0], P._index
 

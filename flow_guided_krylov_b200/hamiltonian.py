@@ -53,7 +53,10 @@ class ProjectedH:
 
     @property
     def nnz(self):
-        return int(getattr(self, "_nnz", None) or self.vals.numel())
+        nz = getattr(self, "_nnz", None)
+        if torch.is_tensor(nz):                 # left on the device by the builder: read once
+            nz = self._nnz = int(nz.item())
+        return int(nz or self.vals.numel())
 
     def _need_csr(self, what):
         if getattr(self, "sell_only", False):
@@ -245,6 +248,30 @@ class ProjectedH:
                            self.row_ptr.cpu().numpy()), shape=(self.n_rows, self.n))
         return M
 
+    def packed_to_coo(self):
+        """(rows, cols, vals) of the packed SELL-32 operator, diagonal entries included (local row
+        ids; FP64 values).  Export / parity helper: plain tensor indexing, not a hot path."""
+        sp, pk, dg = self._sellf
+        dev = pk.device
+        n = self.n_rows
+        lens = getattr(self, "_row_len", None)
+        r = torch.arange(n, device=dev)
+        if lens is None:                        # to_sell_packed(): off-diagonal count = CSR length - 1
+            lens = (self.row_ptr[1:] - self.row_ptr[:-1] - 1).to(torch.int64)
+        lens = lens.to(torch.int64)
+        rows = torch.repeat_interleave(r, lens)
+        start = torch.cumsum(lens, 0) - lens
+        k = torch.arange(rows.shape[0], device=dev) - start[rows]
+        unit = sp[rows // 32] + (k // 2) * 32 + rows % 32
+        half = k % 2
+        flat = pk.view(-1)
+        vals = flat[unit * 4 + half].view(torch.float32).double()
+        cols = flat[unit * 4 + 2 + half].long()
+        rows = torch.cat([r, rows])
+        cols = torch.cat([r + self.row_begin, cols])
+        vals = torch.cat([dg, vals])
+        return rows, cols, vals
+
     def bytes_per_matvec(self, complex_x=False):
         """algorithmic HBM bytes of one product: 12 B/nnz + 20 (36) B/row."""
         return 12 * self.nnz + (36 if complex_x else 20) * self.n_rows
@@ -264,6 +291,9 @@ class BasisIndex:
 
     def __del__(self):
         try:
+            for h in getattr(self, "_lists", {}).values():
+                nat.lib().fgk_strlists_destroy(h)
+            self._lists = {}
             if getattr(self, "_h", None):
                 nat.lib().fgk_index_destroy(self._h)
                 self._h = None
@@ -272,6 +302,17 @@ class BasisIndex:
 
     def __len__(self):
         return self.dets.shape[0]
+
+    def string_lists(self, ham):
+        """single / double replacement lists of the basis' distinct strings for `ham`
+        (fgk_strlists_create), built once per (index, Hamiltonian) pair"""
+        cache = self.__dict__.setdefault("_lists", {})
+        key = id(ham)
+        if key not in cache:
+            h = C.c_void_p()
+            nat.check(nat.lib().fgk_strlists_create(ham._h, self._h, nat.stream_ptr(self.device), C.byref(h)))
+            cache[key] = h
+        return cache[key]
 
     def lookup(self, query):
         query = query.contiguous()
@@ -591,6 +632,106 @@ class MolecularHamiltonian:
         P.sell_only = True
         return P
 
+    PACKED_MAX_STRINGS = 200_000      # the replacement lists are found by an all-pairs string scan
+
+    def projected_packed(self, basis, mode=nat.H_SYM, row_begin=0, row_end=None,
+                         index: Optional[BasisIndex] = None, packed=False, profile=False) -> ProjectedH:
+        """Rows [row_begin,row_end) of the projected H built STRAIGHT into the packed SELL-32
+        operator (exact-float32 off-diagonals + FP64 diagonal, 8 B/nnz): no CSR arrays, no
+        CSR -> SELL pass, no re-pack (fgk_strlists_create + fgk_projh_packed_*; string-driven,
+        one warp per 32-row slice with lane = row).  The operator for Krylov work -- matvec /
+        matvec_host / diagonal / nnz / packed_to_coo; the CSR views (to_dense, to_scipy, sort_rows)
+        need projected_csr.  Row lengths: the bound from the list lengths is taken when a sampled
+        exact count (every 64th slice) confirms it (product bases with dense integrals: no count
+        pass at all), else the exact count pass runs.  Raises if a value is not float32-exact
+        (non-symmetric integrals with H_SYM): use projected_csr(...).to_sell() then."""
+        dets = basis if packed else self.pack(basis)
+        idx = index if index is not None else BasisIndex(dets)
+        self._require_particle_numbers(idx, "projected_packed")
+        n = len(idx)
+        row_end = n if row_end is None else row_end
+        rows = row_end - row_begin
+        dev, st, L = self.device, nat.stream_ptr(self.device), nat.lib()
+        if n == 0 or rows <= 0:
+            raise ValueError("projected_packed: empty row range")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if profile else None
+        if profile:
+            ev[0].record()
+        lists = idx.string_lists(self)
+        if profile:
+            ev[1].record()
+        bound = torch.empty(rows, dtype=torch.int64, device=dev)
+        nat.check(L.fgk_projh_packed_bound(self._h, idx._h, lists, row_begin, row_end, nat.ptr(bound, torch.int64), st))
+        n_slices = (rows + 31) // 32
+        stride = 64 if n_slices >= 256 else 1
+        cnt = bound.clone()
+        nat.check(L.fgk_projh_packed_count(self._h, idx._h, lists, row_begin, row_end, mode, stride,
+                                           nat.ptr(cnt, torch.int64), st))
+        exact_bound = stride > 1 and bool(torch.equal(cnt, bound))          # sampled rows all hit their bound
+        if stride > 1 and not exact_bound:
+            nat.check(L.fgk_projh_packed_count(self._h, idx._h, lists, row_begin, row_end, mode, 1,
+                                               nat.ptr(cnt, torch.int64), st))
+        if profile:
+            ev[2].record()
+        lens = torch.zeros(n_slices * 32, dtype=torch.int64, device=dev)
+        lens[:rows] = cnt
+        width = (lens.view(n_slices, 32).max(dim=1).values + 1) // 2           # pair-columns per slice
+        slice_ptr = torch.zeros(n_slices + 1, dtype=torch.int64, device=dev)   # in 16-byte units
+        torch.cumsum(width * 32, 0, out=slice_ptr[1:])
+        total = int(slice_ptr[-1].item())
+        pk = torch.empty(max(total, 1), 4, dtype=torch.int32, device=dev)
+        diag = self.diag_packed(dets[row_begin:row_end])
+        row_len = torch.empty(rows, dtype=torch.int32, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        if profile:
+            ev[3].record()
+        nat.check(L.fgk_projh_packed_fill(self._h, idx._h, lists, row_begin, row_end, mode,
+                                          nat.ptr(slice_ptr, torch.int64), nat.ptr(pk), nat.ptr(row_len, torch.int32),
+                                          nat.ptr(flag, torch.int32), st))
+        if profile:
+            ev[4].record()
+        if int(flag.item()):
+            raise RuntimeError("projected_packed: an off-diagonal value is not float32-exact (non-symmetric "
+                               "integrals with H_SYM?); use projected_csr(...).to_sell()")
+        row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(row_len.to(torch.int64) + 1, 0, out=row_ptr[1:])
+        empty_c = torch.empty(0, dtype=torch.int32, device=dev)
+        empty_v = torch.empty(0, dtype=torch.float64, device=dev)
+        P = ProjectedH(n, row_ptr, empty_c, empty_v, self.device, row_begin, row_end, mode)
+        P._index = idx
+        P._sellf = (slice_ptr, pk, diag)
+        P._row_len = row_len
+        P._diag_cache = diag
+        P._nnz = row_ptr[-1]
+        P.sell_only = True
+        P.count_pass = "none (list-length bound, confirmed on a sample)" if exact_bound else "exact"
+        if profile:
+            ev[4].synchronize()
+            P.build_profile = {"lists_ms": ev[0].elapsed_time(ev[1]), "bound_count_ms": ev[1].elapsed_time(ev[2]),
+                               "alloc_diag_ms": ev[2].elapsed_time(ev[3]), "fill_ms": ev[3].elapsed_time(ev[4]),
+                               "count_pass": P.count_pass}
+        return P
+
+    def projected_operator(self, basis, mode=nat.H_SYM, row_begin=0, row_end=None,
+                           index: Optional[BasisIndex] = None, packed=False, min_rows=16384) -> ProjectedH:
+        """The projected H in the best storage for repeated H.v (Krylov drivers): built straight
+        into the packed SELL-32 form when the basis is large enough to be bandwidth-bound and its
+        values are float32-exact; CSR (+ optimize_for_matvec) otherwise."""
+        dets = basis if packed else self.pack(basis)
+        idx = index if index is not None else BasisIndex(dets)
+        n = len(idx)
+        re_ = n if row_end is None else row_end
+        if re_ - row_begin >= min_rows:
+            info = idx.info()
+            if max(info["n_alpha_strings"], info["n_beta_strings"]) <= self.PACKED_MAX_STRINGS:
+                try:
+                    return self.projected_packed(dets, mode, row_begin, row_end, index=idx, packed=True)
+                except RuntimeError as e:
+                    if "float32-exact" not in str(e):
+                        raise
+        P = self.projected_csr(dets, mode, row_begin, row_end, index=idx, packed=True, sort_rows=False)
+        return P.optimize_for_matvec()
+
     @torch.no_grad()
     def matrix_elements_fast(self, configs: torch.Tensor) -> torch.Tensor:
         """molecular.py:471-516: dense (n, n), H[i, j] = <i|H|j> raw directed."""
@@ -673,6 +814,6 @@ class MolecularHamiltonian:
         the full particle-conserving space."""
         from .solvers import lowest_eigenpairs
         dets = self.fci_dets()
-        P = self.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)
+        P = self.projected_operator(dets, nat.H_SYM, packed=True)
         w, _ = lowest_eigenpairs(P, k=1)
         return float(w[0])

@@ -74,6 +74,10 @@ class SKQDConfig:
     expand_sources: int = 512              # adaptive: members (largest amplitude) whose connections may enter per round
     expand_new_per_round: int = 262_144    # adaptive: determinants added per growth round at most
     expand_rounds: int = 1                 # adaptive: growth rounds before every time step
+    # False: exp(-i dt H) with the reference's RAW directed elements (skqd.py:390-416; not Hermitian
+    # because of the sign quirk F3, so the norm drifts -- sampling normalises).  True: the
+    # symmetrised 0.5 (H + H^T), a unitary evolution.
+    hermitian_evolution: bool = False
 
 
 def _cfg(config, name):
@@ -146,6 +150,8 @@ class SampleBasedKrylovDiagonalization:
         self._set_subspace(sort_unique_dets(self._seed_dets(), self.hamiltonian.n_orbitals))
 
     def _set_subspace(self, dets):
+        if getattr(self, "_subspace_op", None) is not None:
+            self._subspace_op.close()
         self._subspace_dets = dets.contiguous()
         self._subspace_index = BasisIndex(self._subspace_dets)
         self._subspace_H = None
@@ -203,15 +209,23 @@ class SampleBasedKrylovDiagonalization:
     # :374-419
     def _build_subspace_hamiltonian(self):
         if self._subspace_H is None:
-            if self.adaptive and self._world() > 1:     # rows sharded over the ranks
+            n_set = int(self._subspace_dets.shape[0])
+            if self.adaptive and self._world() > 1 and n_set >= 4096 * self._world():   # rows sharded over the ranks
                 from . import dist as fdist
-                self._subspace_H, self._subspace_op = fdist.build_sharded_h(
-                    self.hamiltonian, self._subspace_dets, nat.H_RAW, index=self._subspace_index)
+                self._subspace_H, _ = fdist.build_sharded_h(
+                    self.hamiltonian, self._subspace_dets, self._evolution_mode(), index=self._subspace_index)
+                self._subspace_H.optimize_for_matvec(min_rows=0)
+                # complex one-launch step: product + peer broadcast + barrier
+                self._subspace_op = fdist.FusedShardedOperator(self._subspace_H)
+                return self._subspace_H
             else:
                 self._subspace_H = self.hamiltonian.projected_csr(
-                    self._subspace_dets, nat.H_RAW, index=self._subspace_index, packed=True)
+                    self._subspace_dets, self._evolution_mode(), index=self._subspace_index, packed=True)
             self._subspace_H.optimize_for_matvec()      # ~30 complex H.v per time step
         return self._subspace_H
+
+    def _evolution_mode(self):
+        return nat.H_SYM if _cfg(self.config, "hermitian_evolution") else nat.H_RAW
 
     def _build_sparse_hamiltonian(self):
         return self._build_subspace_hamiltonian()
@@ -234,6 +248,8 @@ class SampleBasedKrylovDiagonalization:
         for _ in range(num_steps):
             psi = expm_multiply(P, psi, -1j * self.time_step, mu=mu, norm1=nrm,
                                 matvec=None if op is None else op.matvec)
+        if op is not None:
+            op.check()
         return psi
 
     def _subspace_position(self, config: torch.Tensor) -> int:
@@ -333,7 +349,11 @@ class SampleBasedKrylovDiagonalization:
         return self._ground_state_packed(dets, return_eigenvector, regularization)
 
     def _ground_state_packed(self, dets, return_eigenvector=False, regularization=1e-8):
-        P = self.hamiltonian.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)   # :718-734
+        H = self.hamiltonian
+        if dets.shape[0] > DENSE_EIG_MAX:       # Davidson: the operator in its H.v storage
+            P = H.projected_operator(dets, nat.H_SYM, packed=True)
+        else:
+            P = H.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)             # :718-734
         n = P.n
         reg = regularization if regularization > 0 else 0.0                                 # :738-739
         if n <= DENSE_EIG_MAX:

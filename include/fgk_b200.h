@@ -66,6 +66,7 @@ extern "C" {
 typedef struct fgk_ham* fgk_ham_t;
 typedef struct fgk_index* fgk_index_t;
 typedef struct fgk_pt2* fgk_pt2_t;
+typedef struct fgk_strlists* fgk_strlists_t;
 
 int fgk_version(void);
 const char* fgk_last_error(void);
@@ -144,6 +145,35 @@ int fgk_csr_sort_rows(int64_t n_rows, const int64_t* row_ptr, int32_t* cols, dou
  * zero-filled by the caller. */
 int fgk_projh_fill_sell(fgk_ham_t h, fgk_index_t idx, int64_t row_begin, int64_t row_end, int mode,
                         const int64_t* slice_ptr, int32_t* sell_cols, double* sell_vals, void* stream);
+
+/* ---- K5b projected H straight into the packed SELL-32 operator (8 B/nnz) --------------------
+ * Same matrix as fgk_projh_* (molecular.py:471-516, skqd.py:374-419) but assembled string-driven,
+ * one warp per 32-row slice with lane = row, directly in the layout fgk_spmv_sell_f32_* read
+ * (see fgk_sell_pack_f32): no CSR arrays, no CSR -> SELL pass, no re-pack.
+ * fgk_strlists_create builds, once per (Hamiltonian, index) pair, the single / double replacement
+ * lists of the distinct alpha / beta strings of the basis (synchronises `stream` twice to size them;
+ * memory from the library's pool).
+ * Row lengths count OFF-DIAGONAL entries (the diagonal is the separate FP64 array fgk_diag
+ * fills).  fgk_projh_packed_bound: upper bound from the list lengths alone (exact for product
+ * bases with dense integrals).  fgk_projh_packed_count: exact lengths by the same walk, for
+ * the slices s = 0, slice_stride, 2 slice_stride, ... only (other rows' counts are untouched):
+ * stride 1 = every row; a larger stride is a cheap sample to check the bound against.
+ * fgk_projh_packed_fill: slice_ptr (16-byte units) from the caller's row lengths (slice width
+ * = ceil(max length in the slice / 2) pair-columns); writes every unit of every slice (padding
+ * included), row_len[r] = entries written, *flag = 1 if a value was not float32-exact
+ * (non-symmetric integrals with FGK_H_SYM) or a slice was too narrow -- rebuild through
+ * fgk_projh_count / fgk_projh_fill then. */
+int fgk_strlists_create(fgk_ham_t h, fgk_index_t idx, void* stream, fgk_strlists_t* out);
+int fgk_strlists_destroy(fgk_strlists_t lists);
+int fgk_strlists_info(fgk_strlists_t lists, int64_t* n_single_alpha, int64_t* n_double_alpha,
+                      int64_t* n_single_beta, int64_t* n_double_beta);
+int fgk_projh_packed_bound(fgk_ham_t h, fgk_index_t idx, fgk_strlists_t lists, int64_t row_begin,
+                           int64_t row_end, int64_t* counts, void* stream);
+int fgk_projh_packed_count(fgk_ham_t h, fgk_index_t idx, fgk_strlists_t lists, int64_t row_begin,
+                           int64_t row_end, int mode, int64_t slice_stride, int64_t* counts, void* stream);
+int fgk_projh_packed_fill(fgk_ham_t h, fgk_index_t idx, fgk_strlists_t lists, int64_t row_begin,
+                          int64_t row_end, int mode, const int64_t* slice_ptr, void* packed,
+                          int32_t* row_len, int* flag, void* stream);
 
 /* ---- K6 sparse H.v, FP64 CSR ----------------------------------------------------------
  * replaces scipy's csr_matvec inside eigsh (skqd.py:784, residual_expansion.py:435,

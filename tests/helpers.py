@@ -56,7 +56,7 @@ def hostcheck():
     global _hc
     if _hc is None:
         so = os.path.join(CSRC, "libfgk_hostcheck.so")
-        srcs = [os.path.join(CSRC, f) for f in ("fgk_hostcheck.cpp", "fgk_core.cuh", "fgk_tables.h")]
+        srcs = [os.path.join(CSRC, f) for f in ("fgk_hostcheck.cpp", "fgk_core.cuh", "fgk_lists.cuh", "fgk_tables.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-x", "c++", "-std=c++17", "-fPIC", "-shared",
                                    "-o", so, srcs[0]])
@@ -75,6 +75,8 @@ def hostcheck():
         L.hc_bra_row2.argtypes = [vp, vp, i64, i64, ci, ci, vp, vp, i64]
         L.hc_bra_row3.restype = i64
         L.hc_bra_row3.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64]
+        L.hc_bra_row4.restype = i64
+        L.hc_bra_row4.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64]
         L.hc_pt2_walk2.restype = i64
         L.hc_pt2_walk2.argtypes = [vp, u64, u64, vp, vp, i64]
         L.hc_check_split.restype = i64

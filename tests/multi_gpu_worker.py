@@ -44,27 +44,57 @@ def main():
     z = torch.complex(x, torch.flip(x, [0]))
     assert float((op.matvec(z) - Pfull.matvec(z)).abs().max()) < 1e-11
 
-    # fused H.v + all-gather over peer memory: same vectors, several ping-pong steps
-    fop = fd.FusedShardedOperator(Pblk)
+    # one-launch step (product + peer broadcast + barrier): same vectors, several ping-pong steps,
+    # FP64 and packed storage, real and complex vectors
     yref = Pfull.matvec(x)
-    assert float((fop.matvec(x) - yref).abs().max()) < 1e-11
-    fop.load(x)
-    cur = x
-    for _ in range(5):
-        cur = Pfull.matvec(cur)
-        cur = cur / torch.linalg.norm(cur)
-        got = fop.step()
-        got /= torch.linalg.norm(got)          # in-place on the view: every rank scales its own copy
-        assert float((got - cur).abs().max()) < 1e-11
-    wf, _ = lowest_eigenpairs(fop, k=1, matvec=fop.matvec, diagonal=fop.diagonal(), dense_max=0)
-    fop.check()
-    fop.close()
+    zref = Pfull.matvec(z)
+    wf = None
+    for storage in ("sell", "packed"):
+        fop = fd.FusedShardedOperator(Pblk, storage=storage)
+        assert fop.packed == (storage == "packed")
+        assert float((fop.matvec(x) - yref).abs().max()) < 1e-11
+        assert float((fop.matvec(z) - zref).abs().max()) < 1e-11
+        fop.load(x)
+        cur = x
+        for _ in range(5):
+            cur = Pfull.matvec(cur)
+            cur = cur / torch.linalg.norm(cur)
+            got = fop.step()
+            got /= torch.linalg.norm(got)          # in-place on the view: every rank scales its own copy
+            assert float((got - cur).abs().max()) < 1e-11
+        fop.load(z)
+        cz = z
+        for _ in range(3):
+            cz = Pfull.matvec(cz)
+            cz = cz / torch.linalg.norm(cz)
+            got = fop.step()
+            got /= torch.linalg.norm(got)
+            assert got.is_complex() and float((got - cz).abs().max()) < 1e-11
+        # row-sharded input: peer gather + local rows only
+        yl = fop.matvec_local(x[lo:hi].contiguous())
+        assert float((yl - yref[lo:hi]).abs().max()) < 1e-11
+        zl = fop.matvec_local(z[lo:hi].contiguous())
+        assert float((zl - zref[lo:hi]).abs().max()) < 1e-11
+        # host vectors: every rank uploads its slice only
+        yh = fop.matvec_host(x.cpu().pin_memory())
+        assert float((yh.to(dev) - yref[lo:hi]).abs().max()) < 1e-11
+        yh = fop.matvec_host(x.cpu().pin_memory())          # twice: buffers ping-pong
+        assert float((yh.to(dev) - yref[lo:hi]).abs().max()) < 1e-11
+        # replicated Davidson through matvec, row-sharded Davidson through matvec_local
+        wf, _ = lowest_eigenpairs(fop, k=1, matvec=fop.matvec, diagonal=fop.diagonal(), dense_max=0)
+        ws, vs = lowest_eigenpairs(fop, k=2, sharded=fop)
+        fop.check()
+        assert abs(float(wf[0]) - float(ws[0])) < 1e-9
+        res = Pfull.matvec(vs[:, 0].contiguous()) - ws[0] * vs[:, 0]
+        assert float(torch.linalg.norm(res)) < 1e-8
+        fop.close()
 
     # Davidson and Taylor expm through the sharded operator
     w1, v1 = lowest_eigenpairs(Pfull, k=2, dense_max=0)
     w2, v2 = lowest_eigenpairs(op, k=2, matvec=op.matvec, diagonal=op.diagonal(), dense_max=0)
     assert float((w1 - w2).abs().max()) < 1e-9, (w1, w2)
     assert abs(float(wf[0]) - float(w1[0])) < 1e-9
+    assert float((ws - w1).abs().max()) < 1e-9
     psi = torch.zeros(n, dtype=torch.complex128, device=dev)
     psi[0] = 1.0
     e1 = expm_multiply(Pfull, psi, -0.1j)

@@ -153,6 +153,35 @@ def test_rank_based_bra_rows_equal_flat_enumeration(name, mode):
 
 
 @pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_string_driven_bra_rows_equal_flat_enumeration(name, mode):
+    """the string-driven row builder (k_projh4 strategy, fgk_lists.cuh: replacement lists with
+    signed values, rows assembled from list entries) produces exactly the entries of the flat
+    enumeration -- raw, symmetrised, and symmetrised with exact zeros dropped"""
+    g = load_golden("ham_" + name)
+    hc, H, n_orb = make(g)
+    basis = np.unique(np.concatenate([g["basis"], g["dets"]]), axis=0)
+    pk = pack_np(basis, n_orb)
+    n = len(basis)
+    for i in range(0, n, max(1, n // 25)):
+        cap = n + 4
+        c1, v1 = np.zeros(cap, np.int32), np.zeros(cap)
+        c4, v4 = np.zeros(cap, np.int32), np.zeros(cap)
+        m1 = hostcheck().hc_bra_row(hc, _p(pk), n, i, mode & 1, _p(c1), _p(v1), cap)
+        m4 = hostcheck().hc_bra_row4(hc, _p(pk), n, i, mode, _p(c4), _p(v4), cap)
+        if mode & 2:        # FGK_H_DROP_ZEROS: the flat walk keeps explicit zeros (F3 cancellations), drop them here
+            keep = np.ones(m1, bool)
+            keep[1:] = v1[1:m1] != 0.0
+            c1[:keep.sum()], v1[:keep.sum()] = c1[:m1][keep], v1[:m1][keep]
+            m1 = int(keep.sum())
+        assert m1 == m4
+        o1, o4 = np.argsort(c1[:m1], kind="stable"), np.argsort(c4[:m4], kind="stable")
+        assert np.array_equal(c1[:m1][o1], c4[:m4][o4])
+        assert np.array_equal(v1[:m1][o1].view(np.uint64), v4[:m4][o4].view(np.uint64))
+    hostcheck().hc_ham_destroy(hc)
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_pt2_walk_by_singles_lists_equals_reference_connections(name):
     """the PT2 walk of k_pt2_accumulate2 (singles lists, separable alpha-beta elements) emits
     exactly the reference's connections with exactly its float32 elements, in another order"""
