@@ -17,6 +17,7 @@ import torch
 from . import _native as nat
 from .hamiltonian import BasisIndex, sort_unique_dets
 from .solvers import lowest_eigenpairs
+from . import solvers as _solvers
 
 
 @dataclass
@@ -350,23 +351,40 @@ class SelectedCIExpander:
         return tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
 
     # :408-443 -- float64, symmetrised; dense eigh for small n, Davidson above
-    def _diagonalize_packed(self, dets):
+    def _diagonalize_packed(self, dets, warm=None, trusted=False):
+        """-> (E0, v0, index).  The last result is kept: the pipeline's loop calls expand_basis
+        with the basis the previous call returned, whose eigenpair was just computed (the
+        reference recomputes it, residual_expansion.py:356).  warm = (old dets, old eigenvector):
+        start vector for the iterative solver, embedded into the new basis.  trusted: the
+        determinants are a checked basis plus excitations of it (particle numbers conserved)."""
         H = self.hamiltonian
         n = dets.shape[0]
+        c = getattr(self, "_last_diag", None)
+        if c is not None and c[0].shape == dets.shape and bool(torch.equal(c[0], dets)):
+            return c[1], c[2], c[3]
+        index = BasisIndex(dets)
+        if trusted:
+            index._particles_ok = (H.n_alpha, H.n_beta)
+        v0 = None
+        if warm is not None and n > _solvers.DENSE_EIG_MAX:
+            pos = index.lookup(warm[0]).long()
+            v0 = torch.zeros(n, dtype=torch.float64, device=dets.device)
+            v0[pos[pos >= 0]] = warm[1][pos >= 0]
         if self._world() > 1 and n >= self.sharded_min_rows:
             from . import dist as fdist
-            index = BasisIndex(dets)
             Pb, _ = fdist.build_sharded_h(H, dets, nat.H_SYM, index=index, operator=True)   # packed rows, built directly
             op = fdist.FusedShardedOperator(Pb)
             try:
-                w, v = lowest_eigenpairs(op, k=1, sharded=op)   # row-sharded vectors, peer gather per product
+                w, v = lowest_eigenpairs(op, k=1, sharded=op, v0=v0)   # row-sharded vectors, peer gather per product
                 op.check()
             finally:
                 op.close()
-            return float(w[0]), v[:, 0], index
-        P = H.projected_operator(dets, nat.H_SYM, packed=True)     # CSR below 16,384 rows, packed SELL-32 above
-        w, v = lowest_eigenpairs(P, k=1)
-        return float(w[0]), v[:, 0], P._index
+        else:
+            P = H.projected_operator(dets, nat.H_SYM, index=index, packed=True)   # CSR below 16,384 rows, packed SELL-32 above
+            w, v = lowest_eigenpairs(P, k=1, v0=v0)
+        out = (float(w[0]), v[:, 0], index)
+        self._last_diag = (dets,) + out
+        return out
 
     def _diagonalize(self, basis: torch.Tensor) -> Tuple[float, np.ndarray]:
         E, v, _ = self._diagonalize_packed(self.hamiltonian.pack(basis))
@@ -375,11 +393,20 @@ class SelectedCIExpander:
     # :451-554
     def _find_important_packed(self, dets, index, energy, v):
         H = self.hamiltonian
-        if self._world() > 1:
+        # the workspace is kept between rounds (allocation + first-touch of a fresh table cost more
+        # than a small sweep); every sharded rank sizes it for its share of the sources
+        world = self._world()
+        need = default_pt2_capacity(H, -(-int(dets.shape[0]) // world))
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.capacity < need or str(ws.device) != str(H.device):
+            ws = self._ws = Pt2Workspace(int(need * 1.5) if need < (1 << 24) else need, H.device)
+        if world > 1:
             from . import dist as fdist
-            sel, imp, st = fdist.pt2_select_sharded(H, index, v, energy, self.config.max_configs_per_iter)
+            sel, imp, st = fdist.pt2_select_sharded(H, index, v, energy, self.config.max_configs_per_iter, workspace=ws)
         else:
-            sel, imp, st = pt2_select(H, index, v, energy, self.config.max_configs_per_iter)
+            sel, imp, st = pt2_select(H, index, v, energy, self.config.max_configs_per_iter, workspace=ws)
+        if ws.capacity > (1 << 24):             # large sweeps: give the memory back for the next H build
+            self._ws = None
         self.last_stats = st
         return sel, imp
 
@@ -404,9 +431,11 @@ class SelectedCIExpander:
             return current_basis, {'configs_added': 0, 'energy': energy, 'initial_energy': energy,
                                    'final_energy': energy}
         expanded = sort_unique_dets(torch.cat([dets, sel], dim=0), H.n_orbitals)   # :367-368
-        new_energy, _, _ = self._diagonalize_packed(expanded)                    # :371
+        keep_old = getattr(self, "_last_diag", None)
+        new_energy, _, _ = self._diagonalize_packed(expanded, warm=(dets, v), trusted=True)   # :371
         energy_improvement = energy - new_energy
         if energy_improvement < -1e-8:                                           # :378-393
+            self._last_diag = keep_old          # the caller keeps the old basis
             return current_basis, {
                 'initial_size': len(current_basis), 'final_size': len(current_basis),
                 'configs_added': 0, 'initial_energy': energy, 'final_energy': energy,

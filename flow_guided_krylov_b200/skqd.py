@@ -38,7 +38,8 @@ import torch
 
 from . import _native as nat
 from .hamiltonian import BasisIndex, sort_unique_dets
-from .solvers import expm_multiply, lowest_eigenpairs, DENSE_EIG_MAX
+from . import solvers as _solvers
+from .solvers import expm_multiply, lowest_eigenpairs
 
 try:
     from tqdm import tqdm
@@ -350,13 +351,13 @@ class SampleBasedKrylovDiagonalization:
 
     def _ground_state_packed(self, dets, return_eigenvector=False, regularization=1e-8):
         H = self.hamiltonian
-        if dets.shape[0] > DENSE_EIG_MAX:       # Davidson: the operator in its H.v storage
+        if dets.shape[0] > _solvers.DENSE_EIG_MAX:       # Davidson: the operator in its H.v storage
             P = H.projected_operator(dets, nat.H_SYM, packed=True)
         else:
             P = H.projected_csr(dets, nat.H_SYM, packed=True, sort_rows=False)             # :718-734
         n = P.n
         reg = regularization if regularization > 0 else 0.0                                 # :738-739
-        if n <= DENSE_EIG_MAX:
+        if n <= _solvers.DENSE_EIG_MAX:
             D = P.to_dense()
             D = 0.5 * (D + D.T) + reg * torch.eye(n, dtype=torch.float64, device=D.device)
             w, v = torch.linalg.eigh(D)

@@ -43,7 +43,7 @@ class _Phases:
 
 
 def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=None,
-                      diagonal=None, dense_max=DENSE_EIG_MAX, v0=None, phases=None, sharded=None):
+                      diagonal=None, dense_max=None, v0=None, phases=None, sharded=None):
     """k lowest eigenpairs of the symmetric operator P (a ProjectedH built with
     H_SYM, or any object with .n plus `matvec`/`diagonal` callables).
     Returns (w (k,) float64 tensor ascending, V (n,k)).
@@ -57,6 +57,8 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
     sharded = a dist.FusedShardedOperator: the ROW-SHARDED form of the same iteration (see
     _davidson_sharded) -- every rank keeps only its row block of the basis vectors."""
     import numpy as np
+    if dense_max is None:
+        dense_max = DENSE_EIG_MAX                  # read at call time (tunable)
     if sharded is not None:
         return _davidson_sharded(sharded, min(k, P.n), tol, max_iter, max_space, v0, phases)
     n = P.n
@@ -121,23 +123,37 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
             T[np.arange(q), np.arange(q)] = th[:q]
             m = q
         added = 0
+        norms = []
         for i in todo:
             den = thk[i] - diag
             den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
             t = R[i] / den
             for _ in range(2):                      # CGS2 against everything kept so far
                 t = t - (V[:m + added] @ t) @ V[:m + added]
-            nt = float(torch.linalg.norm(t))
-            if nt > 1e-10:
-                V[m + added] = t / nt
-                added += 1
+            nt = torch.linalg.norm(t)
+            norms.append(nt)
+            # normalised on the device; a vanished correction (nt ~ 0) is detected from the norm
+            # that comes back with the projection below, and dropped then
+            V[m + added] = t * torch.where(nt > 1e-10, 1.0 / nt, torch.zeros_like(nt))   # zero row if vanished
+            added += 1
         ph.mark("correction_orth")
-        if added == 0:
-            break
         for j in range(m, m + added):
             W[j] = mv(V[j])
         ph.mark("matvec")
-        blk = (V[:m + added] @ W[m:m + added].T).cpu().numpy()     # new columns of T
+        blk_dev = V[:m + added] @ W[m:m + added].T                  # new columns of T
+        back = torch.cat([blk_dev.reshape(-1), torch.stack(norms)]).cpu().numpy()   # ONE read-back
+        blk = back[:blk_dev.numel()].reshape(blk_dev.shape)
+        ok = back[blk_dev.numel():] > 1e-10
+        if not ok.all():                            # drop vanished corrections (rare: breakdown)
+            good = [j for j in range(added) if ok[j]]
+            if not good:
+                break
+            sel = torch.tensor([m + j for j in good], device=dev)
+            V[m:m + len(good)] = V[sel]
+            W[m:m + len(good)] = W[sel]
+            rows = list(range(m)) + [m + j for j in good]
+            blk = blk[np.ix_(rows, good)]
+            added = len(good)
         T[:m + added, m:m + added] = blk
         T[m:m + added, :m + added] = blk.T
         m += added

@@ -216,15 +216,26 @@ def test_projected_packed_direct_build(fgk, name):
     idx = fgk.BasisIndex(dets)
     for mode in (fgk.H_RAW, fgk.H_SYM, fgk.H_SYM | fgk.H_DROP_ZEROS):
         Pc = H.projected_csr(dets, mode, index=idx, packed=True)
-        Pp = H.projected_packed(dets, mode, index=idx, packed=True)
+        try:
+            Pp = H.projected_packed(dets, mode, index=idx, packed=True)
+        except RuntimeError as e:
+            # integrals that are not symmetric to the last float32 bit (N2 from the RHF front-end):
+            # 0.5 (<i|H|j> + <j|H|i>) is then not a float32 number -- the re-pack of the CSR operator
+            # must refuse for the same reason, and projected_operator falls back to FP64 storage
+            assert "float32-exact" in str(e) and mode != fgk.H_RAW
+            with pytest.raises(RuntimeError):
+                H.projected_csr(dets, mode, index=idx, packed=True).to_sell_packed()
+            Pf = H.projected_operator(dets, mode, index=idx, packed=True, min_rows=1)
+            assert not getattr(Pf, "sell_only", False) and getattr(Pf, "_sell", None) is not None
+            continue
         assert Pp.sell_only and Pp.count_pass == "exact"          # small basis: no sampling
         _packed_equals_csr(Pp, Pc)
     if n > 40:
         lo, hi = n // 3, n - 5
-        _packed_equals_csr(H.projected_packed(dets, fgk.H_SYM, row_begin=lo, row_end=hi, index=idx, packed=True),
-                           H.projected_csr(dets, fgk.H_SYM, row_begin=lo, row_end=hi, index=idx, packed=True))
+        _packed_equals_csr(H.projected_packed(dets, fgk.H_RAW, row_begin=lo, row_end=hi, index=idx, packed=True),
+                           H.projected_csr(dets, fgk.H_RAW, row_begin=lo, row_end=hi, index=idx, packed=True))
     with pytest.raises(RuntimeError):
-        H.projected_packed(dets, fgk.H_SYM, index=idx, packed=True).to_dense()
+        H.projected_packed(dets, fgk.H_RAW, index=idx, packed=True).to_dense()
 
 
 def test_projected_packed_bound_and_sampling(fgk):
