@@ -431,3 +431,53 @@ extern "C" int fgk_spmv_sell_f32_z(int64_t n_rows, int64_t row_offset, const int
 {
     return launch_spmv_sell_f32<true>(n_rows, row_offset, slice_ptr, packed, diag, x, y, device, stream);
 }
+
+// ======================================================================================
+// One Taylor term of exp(t (H - mu)) psi (solvers.expm_multiply, reference skqd.py:291-293):
+//   B <- c (y - mu B)   with y = H B already computed,   F <- F + B,
+// and the two infinity norms the truncation test needs, max |B_i| and max |F_i|, folded into
+// norms[0..1] with atomicMax on the bit patterns of the (non-negative) moduli.  One pass over
+// three complex vectors instead of six elementwise kernels and two reductions.
+// ======================================================================================
+__global__ void __launch_bounds__(256)
+k_taylor_update_z(i64 n, const double2* __restrict__ y, double2* __restrict__ B, double2* __restrict__ F,
+                  double mu, double c_re, double c_im, unsigned long long* norms)
+{
+    double mb = 0.0, mf = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double2 yi = y[i], bi = B[i];
+        const double ur = yi.x - mu * bi.x, ui = yi.y - mu * bi.y;
+        const double2 nb = make_double2(c_re * ur - c_im * ui, c_re * ui + c_im * ur);
+        double2 f = F[i];
+        f.x += nb.x;
+        f.y += nb.y;
+        B[i] = nb;
+        F[i] = f;
+        mb = fmax(mb, hypot(nb.x, nb.y));
+        mf = fmax(mf, hypot(f.x, f.y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(norms, (unsigned long long)__double_as_longlong(mb));
+        atomicMax(norms + 1, (unsigned long long)__double_as_longlong(mf));
+    }
+}
+
+extern "C" int fgk_taylor_update_z(int64_t n, const double* y, double* B, double* F, double mu, double c_re,
+                                   double c_im, double* norms, int device, void* stream)
+{
+    if (n == 0) return FGK_OK;
+    if (!y || !B || !F || !norms || n < 0) return fgk_fail(FGK_ERR_ARG, "fgk_taylor_update_z: bad argument");
+    FGK_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FGK_CUDA(cudaMemsetAsync(norms, 0, 2 * sizeof(double), st));
+    i64 need = (n + 255) / 256, cap = (i64)fgk_sm_count(device) * 8;
+    k_taylor_update_z<<<(int)(need < cap ? need : cap), 256, 0, st>>>(
+        n, (const double2*)y, (double2*)B, (double2*)F, mu, c_re, c_im, (unsigned long long*)norms);
+    FGK_LAUNCH_CHECK();
+    return FGK_OK;
+}

@@ -730,7 +730,7 @@ class MolecularHamiltonian:
                     if "float32-exact" not in str(e):
                         raise
         P = self.projected_csr(dets, mode, row_begin, row_end, index=idx, packed=True, sort_rows=False)
-        return P.optimize_for_matvec()
+        return P.optimize_for_matvec(min_rows=min_rows)
 
     @torch.no_grad()
     def matrix_elements_fast(self, configs: torch.Tensor) -> torch.Tensor:

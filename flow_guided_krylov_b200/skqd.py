@@ -244,10 +244,14 @@ class SampleBasedKrylovDiagonalization:
                 import torch.distributed as tdist
                 tdist.all_reduce(cs)
             cs = cs - d.abs() + (d - mu).abs()
-            self._expm_cache = (mu, float(cs.max()))
-        mu, nrm = self._expm_cache
+            mvf = P.matvec if op is None else op.matvec
+            # spectral radius of H - mu by power iteration (12 products, once per operator): the
+            # Taylor scaling then follows the spectrum instead of the much larger 1-norm
+            rho = _solvers.spectral_radius_estimate(mvf, P.n, mu, self.device) if P.n > 1 else 0.0
+            self._expm_cache = (mu, float(cs.max()), rho)
+        mu, nrm, rho = self._expm_cache
         for _ in range(num_steps):
-            psi = expm_multiply(P, psi, -1j * self.time_step, mu=mu, norm1=nrm,
+            psi = expm_multiply(P, psi, -1j * self.time_step, mu=mu, norm1=nrm, rho=rho,
                                 matvec=None if op is None else op.matvec)
         if op is not None:
             op.check()

@@ -257,6 +257,12 @@ int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* const* peer_ds
                     uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
                     uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
 
+/* One Taylor term of exp(t (H - mu I)) psi (scipy expm_multiply under skqd.py:291-293), complex128
+ * vectors of length n: B <- c (y - mu B) with y = H B, F <- F + B; norms[0] = max |B_i|,
+ * norms[1] = max |F_i| (device double[2], written by the call). */
+int fgk_taylor_update_z(int64_t n, const double* y, double* B, double* F, double mu, double c_re,
+                        double c_im, double* norms, int device, void* stream);
+
 /* ---- K7/K8 PT2 residual expansion --------------------------------------------------------
  * replaces SelectedCIExpander._find_important_configs (residual_expansion.py:451-554)
  * and ResidualBasedExpander._find_residual_configs (:174-253).
