@@ -138,6 +138,29 @@ def main():
     assert abs(st1["final_energy"] - st3["final_energy"]) < 1e-9
     assert abs(st2["final_energy"] - st3["final_energy"]) < 1e-9
     assert st3["configs_added"] == 150
+    # Stage 4 on a growing determinant set (adaptive SKQD): rows of H_S sharded, complex one-launch
+    # step for exp(-i dt H_S), growth by the sharded MAXABS selection -- same sets, same amplitudes
+    # and same energies as the single-process run
+    cfg = fgk.SKQDConfig(max_krylov_dim=3, shots_per_krylov=4000, subspace_mode="adaptive",
+                         max_subspace_size=24000, expand_sources=48, expand_new_per_round=16000)
+    nf = H.unpack(dets[torch.randperm(n, generator=torch.Generator().manual_seed(4))[:300].to(dev)].contiguous())
+    fgk.SampleBasedKrylovDiagonalization._world = staticmethod(lambda: wsz)
+    torch.manual_seed(5)
+    sk_n = fgk.FlowGuidedSKQD(H, nf, cfg)
+    res_n = sk_n.run_with_nf(progress=False)
+    assert sk_n._subspace_op is not None            # the sharded branch ran
+    fgk.SampleBasedKrylovDiagonalization._world = staticmethod(lambda: 1)
+    torch.manual_seed(5)
+    sk_1 = fgk.FlowGuidedSKQD(H, nf, cfg)
+    res_1 = sk_1.run_with_nf(progress=False)
+    assert sk_n.subspace_history == sk_1.subspace_history and sk_n.subspace_history[-1] >= 4096 * wsz
+    assert torch.equal(sk_n._subspace_dets, sk_1._subspace_dets)
+    for a, b in zip(sk_n.krylov_states, sk_1.krylov_states):
+        assert float((a - b).abs().max()) < 1e-11
+    for a, b in zip(sk_n.krylov_sample_dets, sk_1.krylov_sample_dets):
+        assert torch.equal(a, b)
+    assert np.abs(np.array(res_n["energies_combined"]) - np.array(res_1["energies_combined"])).max() < 1e-9
+    sk_n._subspace_op.close()
     dist.barrier()
     if rank == 0:
         print(f"MULTI_GPU_OK world={world} n={n} nnz={Pfull.nnz} raw={st_ref['raw_candidates']}")

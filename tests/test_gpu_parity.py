@@ -1194,6 +1194,9 @@ def test_config5_shape_pt2_pass_invariance(fgk):
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from bench import synth_integrals as bench_integrals, cas_window_basis
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()            # blocks the caching allocator kept from earlier tests
     if torch.cuda.mem_get_info()[0] < 80e9:
         pytest.skip("needs ~60 GB of free HBM")
     n_orb = 48
