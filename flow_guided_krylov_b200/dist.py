@@ -188,7 +188,7 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
     expansion.pt2_select."""
     from . import _native as nat
     from .expansion import (Pt2Workspace, _raw_connections_per_det, default_pt2_workspace,
-                            pt2_select, select_top_k)
+                            planned_passes, pt2_select, select_top_k)
     mode = nat.PT2_SUM if mode is None else mode
     rank, ws = world()
     if ws == 1:
@@ -210,7 +210,7 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
     # every rank must run the same number of bucket passes: size them for the smallest workspace
     cap = int(-allreduce_scalar(-float(wa.capacity), "max", dev))
     raw_ub = n_src * _raw_connections_per_det(ham)
-    local_passes = max(1, -(-raw_ub // (2 * cap * ws)))
+    local_passes = planned_passes(raw_ub, cap, ws)
     qp = int(-allreduce_scalar(-float(wa.queue_pairs), "max", dev))
     if qp:
         local_passes = max(local_passes, -(-raw_ub // (qp * ws)))
@@ -265,6 +265,7 @@ class FusedShardedOperator:
     matvec_host uploads only this rank's slice of a host vector."""
 
     ERR_POLL = 64          # steps between looks at the barrier's error flag
+    AR_SLOT = 4096         # doubles per rank in one all-reduce (fgk_peer_allreduce_sum)
 
     def __init__(self, P, group=None, storage="auto"):
         import ctypes as C
@@ -287,9 +288,10 @@ class FusedShardedOperator:
         L = nat.lib()
         nbytes = 16 * self.n                    # room for a complex128 vector
         own, handles = [], []
-        for _ in range(3):                     # two vector buffers + the flag array
+        sizes = [nbytes, nbytes, 8 * 64, 8 * 2 * self.world * self.AR_SLOT]
+        for b in range(4):                     # two vector buffers, the flag array, the all-reduce scratch
             ptr, h = C.c_void_p(), C.create_string_buffer(64)
-            nat.check(L.fgk_peer_alloc(nbytes if len(own) < 2 else 8 * 64, self.dev, C.byref(ptr), h))
+            nat.check(L.fgk_peer_alloc(sizes[b], self.dev, C.byref(ptr), h))
             own.append(ptr.value)
             handles.append(h.raw)
         self._own = own
@@ -299,9 +301,9 @@ class FusedShardedOperator:
         else:
             allh = [handles]
         self._opened = []
-        ptrs = [[0] * self.world for _ in range(3)]
+        ptrs = [[0] * self.world for _ in range(4)]
         for p in range(self.world):
-            for b in range(3):
+            for b in range(4):
                 if p == self.rank:
                     ptrs[b][p] = own[b]
                 else:
@@ -312,6 +314,8 @@ class FusedShardedOperator:
         VP = C.c_void_p * self.world
         self._bufs = [VP(*ptrs[0]), VP(*ptrs[1])]
         self._flags = VP(*ptrs[2])
+        self._scratch = VP(*ptrs[3])
+        self._ar_calls = 0
         self._views = [torch.as_tensor(_DevArray(own[b], self.n), device=P.device) for b in range(2)]
         self._zviews = [torch.as_tensor(_DevArray(own[b], self.n, "<c16"), device=P.device) for b in range(2)]
         self._err = torch.zeros(1, dtype=torch.int64, device=P.device)
@@ -398,6 +402,23 @@ class FusedShardedOperator:
         # call ahead cannot touch the vector this rank's product is still reading
         self._cur = 1 - self._cur
         return y
+
+    def allreduce_sum_(self, t):
+        """in-place sum over the ranks of a small contiguous float64 tensor (the dot products of a
+        row-sharded iteration): one launch over peer memory, identical bits on every rank"""
+        import ctypes as C
+        from . import _native as nat
+        if self.world == 1:
+            return t
+        if t.dtype != torch.float64 or not t.is_contiguous() or t.numel() > self.AR_SLOT:
+            dist.all_reduce(t)
+            return t
+        area = self._ar_calls & 1
+        self._ar_calls += 1
+        nat.check(nat.lib().fgk_peer_allreduce_sum(
+            C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(t.data_ptr()), self._scratch, self.AR_SLOT, area,
+            *self._sync_args()))
+        return t
 
     def check(self):
         e = int(self._err.item())

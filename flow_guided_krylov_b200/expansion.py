@@ -247,19 +247,27 @@ def pt2_candidates(ham, index, coeffs, energy, workspace=None, mode=nat.PT2_SUM,
     return tuple(torch.cat([o[i] for o in outs]) for i in range(4)) + (stats,)
 
 
+DISTINCT_PER_RAW = 0.75     # planning figure: distinct candidates per raw connection (measured 0.37 on
+                            # the configs[3] sweep, 0.60 at configs[4] shape); a wrong guess costs a repeated sweep
+
+
 def default_pt2_capacity(ham, n_sources, partition=False):
-    """distinct-candidate capacity for a sweep over n_sources determinants.  Small sweeps: every
-    raw connection could be a distinct candidate.  Large sweeps: half of the raw connections
-    (measured 0.37 distinct per raw connection on the configs[3] sweep, 0.2 on configs[4]); a
-    sweep that does not fit is split into bucket passes by the callers.  Bounded by the free HBM;
-    per unit of capacity: 16 B table + 32 B pool + 24 B head buffers, plus 2 x 30 B of partition
-    queue."""
+    """distinct-candidate capacity for a sweep over n_sources determinants: every raw connection
+    up to 2^28 of them (small and medium sweeps never need a second pass), DISTINCT_PER_RAW of
+    them above; bounded by the free HBM (a sweep that does not fit is split into bucket passes by
+    the callers).  Per unit of capacity: 16 B table + 32 B pool + 24 B head buffers, plus 2 x 30 B
+    of partition queue."""
     n_conn = _raw_connections_per_det(ham)
     raw = n_sources * n_conn
-    want = raw if raw <= (1 << 24) else max(1 << 24, raw // 2)
+    want = raw if raw <= (1 << 28) else max(1 << 28, int(DISTINCT_PER_RAW * raw))
     free = nat.device_info(ham.device)["free_bytes"]
     per = 72 + (60 if partition else 0) + 8
     return int(min(max(4096, 1.05 * want), 0.8 * free / per, 2 ** 32 - 8))
+
+
+def planned_passes(raw_upper_bound, capacity, shares=1):
+    """bucket passes (per rank) so that the expected distinct candidates of a pass fit the workspace"""
+    return max(1, -(-int(DISTINCT_PER_RAW * raw_upper_bound) // (int(capacity) * shares)))
 
 
 def default_pt2_workspace(ham, n_sources, partition=False):
@@ -289,10 +297,10 @@ def pt2_select(ham, index, coeffs, energy, k, workspace=None, mode=nat.PT2_SUM, 
         return (torch.empty(0, 2, dtype=torch.int64, device=dev),
                 torch.empty(0, dtype=torch.float64, device=dev), stats)
     ws = workspace if workspace is not None else default_pt2_workspace(ham, int(src.numel()))
-    # first guess: half of the raw connections are distinct candidates; with a partition queue
-    # every raw candidate of a pass must also fit the queue
+    # first guess from the planning ratio; with a partition queue every raw candidate of a pass
+    # must also fit the queue
     raw_ub = int(src.numel()) * _raw_connections_per_det(ham)
-    n_pass = max(1, -(-raw_ub // (2 * ws.capacity)))
+    n_pass = planned_passes(raw_ub, ws.capacity)
     if ws.queue_pairs:
         n_pass = max(n_pass, -(-raw_ub // ws.queue_pairs))
     while True:

@@ -641,9 +641,11 @@ class MolecularHamiltonian:
         CSR -> SELL pass, no re-pack (fgk_strlists_create + fgk_projh_packed_*; string-driven,
         one warp per 32-row slice with lane = row).  The operator for Krylov work -- matvec /
         matvec_host / diagonal / nnz / packed_to_coo; the CSR views (to_dense, to_scipy, sort_rows)
-        need projected_csr.  Row lengths: the bound from the list lengths is taken when a sampled
-        exact count (every 64th slice) confirms it (product bases with dense integrals: no count
-        pass at all), else the exact count pass runs.  Raises if a value is not float32-exact
+        need projected_csr.  Row lengths: a PRODUCT basis (every alpha string paired with every beta
+        string: CAS windows, full spaces) is filled straight into storage sized by the bound from the
+        list lengths -- no count pass at all; only if filtered values leave more than 2 % padding
+        (real molecules: symmetry zeros) it is refilled with the lengths the first fill measured.
+        Other bases run the exact count pass.  Raises if a value is not float32-exact
         (non-symmetric integrals with H_SYM): use projected_csr(...).to_sell() then."""
         dets = basis if packed else self.pack(basis)
         idx = index if index is not None else BasisIndex(dets)
@@ -660,39 +662,47 @@ class MolecularHamiltonian:
         lists = idx.string_lists(self)
         if profile:
             ev[1].record()
-        bound = torch.empty(rows, dtype=torch.int64, device=dev)
-        nat.check(L.fgk_projh_packed_bound(self._h, idx._h, lists, row_begin, row_end, nat.ptr(bound, torch.int64), st))
-        n_slices = (rows + 31) // 32
-        stride = 64 if n_slices >= 256 else 1
-        cnt = bound.clone()
-        nat.check(L.fgk_projh_packed_count(self._h, idx._h, lists, row_begin, row_end, mode, stride,
-                                           nat.ptr(cnt, torch.int64), st))
-        exact_bound = stride > 1 and bool(torch.equal(cnt, bound))          # sampled rows all hit their bound
-        if stride > 1 and not exact_bound:
+        info = idx.info()
+        product = info["dense_pairs"] and n == info["n_alpha_strings"] * info["n_beta_strings"]
+        cnt = torch.empty(rows, dtype=torch.int64, device=dev)
+        if product:     # every string pair is a determinant: the bound can only be missed through filtered values
+            nat.check(L.fgk_projh_packed_bound(self._h, idx._h, lists, row_begin, row_end, nat.ptr(cnt, torch.int64), st))
+        else:
             nat.check(L.fgk_projh_packed_count(self._h, idx._h, lists, row_begin, row_end, mode, 1,
                                                nat.ptr(cnt, torch.int64), st))
         if profile:
             ev[2].record()
-        lens = torch.zeros(n_slices * 32, dtype=torch.int64, device=dev)
-        lens[:rows] = cnt
-        width = (lens.view(n_slices, 32).max(dim=1).values + 1) // 2           # pair-columns per slice
-        slice_ptr = torch.zeros(n_slices + 1, dtype=torch.int64, device=dev)   # in 16-byte units
-        torch.cumsum(width * 32, 0, out=slice_ptr[1:])
-        total = int(slice_ptr[-1].item())
-        pk = torch.empty(max(total, 1), 4, dtype=torch.int32, device=dev)
+        n_slices = (rows + 31) // 32
         diag = self.diag_packed(dets[row_begin:row_end])
-        row_len = torch.empty(rows, dtype=torch.int32, device=dev)
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        if profile:
-            ev[3].record()
-        nat.check(L.fgk_projh_packed_fill(self._h, idx._h, lists, row_begin, row_end, mode,
-                                          nat.ptr(slice_ptr, torch.int64), nat.ptr(pk), nat.ptr(row_len, torch.int32),
-                                          nat.ptr(flag, torch.int32), st))
+        count_pass = "none (list-length bound of a product basis)" if product else "exact"
+        for attempt in range(2):
+            lens = torch.zeros(n_slices * 32, dtype=torch.int64, device=dev)
+            lens[:rows] = cnt
+            width = (lens.view(n_slices, 32).max(dim=1).values + 1) // 2           # pair-columns per slice
+            slice_ptr = torch.zeros(n_slices + 1, dtype=torch.int64, device=dev)   # in 16-byte units
+            torch.cumsum(width * 32, 0, out=slice_ptr[1:])
+            total = int(slice_ptr[-1].item())
+            pk = torch.empty(max(total, 1), 4, dtype=torch.int32, device=dev)
+            row_len = torch.empty(rows, dtype=torch.int32, device=dev)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            if profile and attempt == 0:
+                ev[3].record()
+            nat.check(L.fgk_projh_packed_fill(self._h, idx._h, lists, row_begin, row_end, mode,
+                                              nat.ptr(slice_ptr, torch.int64), nat.ptr(pk), nat.ptr(row_len, torch.int32),
+                                              nat.ptr(flag, torch.int32), st))
+            # one read-back: inexact / too-narrow flag, and how much of the bound-sized storage is padding
+            wasteful = (row_len.sum() * 50 < cnt.sum() * 49).to(torch.int32).reshape(1)
+            bad, waste = torch.cat([flag, wasteful]).tolist()
+            if bad:
+                raise RuntimeError("projected_packed: an off-diagonal value is not float32-exact (non-symmetric "
+                                   "integrals with H_SYM?); use projected_csr(...).to_sell()")
+            if not (product and waste and attempt == 0):
+                break
+            cnt = row_len.to(torch.int64)       # > 2 % padding (filtered values): refill with the exact lengths
+            count_pass = "the first fill (bound-sized) served as the count pass"
+            del pk
         if profile:
             ev[4].record()
-        if int(flag.item()):
-            raise RuntimeError("projected_packed: an off-diagonal value is not float32-exact (non-symmetric "
-                               "integrals with H_SYM?); use projected_csr(...).to_sell()")
         row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
         torch.cumsum(row_len.to(torch.int64) + 1, 0, out=row_ptr[1:])
         empty_c = torch.empty(0, dtype=torch.int32, device=dev)
@@ -704,7 +714,7 @@ class MolecularHamiltonian:
         P._diag_cache = diag
         P._nnz = row_ptr[-1]
         P.sell_only = True
-        P.count_pass = "none (list-length bound, confirmed on a sample)" if exact_bound else "exact"
+        P.count_pass = count_pass
         if profile:
             ev[4].synchronize()
             P.build_profile = {"lists_ms": ev[0].elapsed_time(ev[1]), "bound_count_ms": ev[1].elapsed_time(ev[2]),

@@ -182,8 +182,12 @@ def _davidson_sharded(op, k, tol, max_iter, max_space, v0, phases):
     ph.mark(None)
     multi = op.world > 1
 
+    peer_sum = getattr(op, "allreduce_sum_", None)      # dist.FusedShardedOperator: one launch over peer memory
+
     def allsum(t):
         if multi:
+            if peer_sum is not None:
+                return peer_sum(t.contiguous())
             tdist.all_reduce(t)
         return t
 
@@ -214,6 +218,11 @@ def _davidson_sharded(op, k, tol, max_iter, max_space, v0, phases):
     T[:m, :m] = allsum(V[:m] @ W[:m].T).cpu().numpy()
     w_out = X = None
     ph.mark("setup")
+    # One host synchronisation and three small all-reduces per iteration: the residual norms of
+    # the Ritz vectors travel with the first orthogonalisation pass and are LOOKED AT one
+    # iteration late (together with the projection block), so a converged solve spends one extra
+    # product instead of a read-back per iteration.
+    rn_prev = np.full(k, np.inf)
     for _ in range(max_iter):
         Tm = 0.5 * (T[:m, :m] + T[:m, :m].T)
         th, s = np.linalg.eigh(Tm)
@@ -221,13 +230,11 @@ def _davidson_sharded(op, k, tol, max_iter, max_space, v0, phases):
         thk = torch.from_numpy(th[:k].copy()).to(dev)
         X = s_dev[:k] @ V[:m]
         R = s_dev[:k] @ W[:m] - thk[:, None] * X
-        rn = torch.sqrt(allsum((R * R).sum(dim=1))).cpu().numpy()
+        rr_local = (R * R).sum(dim=1)
         ph.mark("ritz_residual")
         w_out = thk
         scale = max(1.0, float(np.abs(th[:k]).max()))
-        if rn.max() < tol * scale:
-            break
-        todo = [i for i in range(k) if rn[i] >= tol * scale]
+        todo = [i for i in range(k) if rn_prev[i] >= tol * scale]
         if m + len(todo) > m_max:
             q = keep
             V[:q] = s_dev[:q] @ V[:m]
@@ -236,24 +243,47 @@ def _davidson_sharded(op, k, tol, max_iter, max_space, v0, phases):
             T[np.arange(q), np.arange(q)] = th[:q]
             m = q
         added = 0
+        norms = []
+        rr_glob = None
         for i in todo:
             den = thk[i] - diag
             den = torch.where(den.abs() < 1e-8, torch.full_like(den, -1e-8), den)
             t = R[i] / den
-            for _ in range(2):                           # CGS2, coefficients summed over the ranks
-                c = allsum(V[:m + added] @ t)
-                t = t - c @ V[:m + added]
-            nt = float(torch.sqrt(allsum((t * t).sum().reshape(1)))[0])
-            if nt > 1e-10:
-                V[m + added] = t / nt
-                added += 1
+            # pass 1 (+ all residual norms on the first correction), pass 2 (+ t.t: the norm after the
+            # pass follows from Pythagoras, V is orthonormal)
+            buf = allsum(torch.cat([V[:m + added] @ t, rr_local if rr_glob is None else rr_local[:0]]))
+            if rr_glob is None:
+                rr_glob = buf[m + added:]
+            t = t - buf[:m + added] @ V[:m + added]
+            buf = allsum(torch.cat([V[:m + added] @ t, (t * t).sum().reshape(1)]))
+            c2 = buf[:m + added]
+            t = t - c2 @ V[:m + added]
+            nt = torch.sqrt(torch.clamp(buf[m + added] - (c2 * c2).sum(), min=0.0))
+            norms.append(nt)
+            V[m + added] = t * torch.where(nt > 1e-10, 1.0 / nt, torch.zeros_like(nt))
+            added += 1
         ph.mark("correction_orth")
-        if added == 0:
-            break
         for j in range(m, m + added):
             op.matvec_local(V[j], out=W[j])
         ph.mark("matvec")
-        blk = allsum(V[:m + added] @ W[m:m + added].T).cpu().numpy()
+        blk_dev = allsum(V[:m + added] @ W[m:m + added].T)
+        back = torch.cat([blk_dev.reshape(-1), torch.stack(norms), rr_glob]).cpu().numpy()   # ONE read-back
+        nb_ = blk_dev.numel()
+        blk = back[:nb_].reshape(blk_dev.shape)
+        ok = back[nb_:nb_ + added] > 1e-10
+        rn_prev = np.sqrt(np.maximum(back[nb_ + added:], 0.0))
+        if rn_prev.max() < tol * scale:
+            break                                   # (w_out, X) of this iteration's Ritz step are converged
+        if not ok.all():                            # drop vanished corrections (rare: breakdown)
+            good = [j for j in range(added) if ok[j]]
+            if not good:
+                break
+            sel = torch.tensor([m + j for j in good], device=dev)
+            V[m:m + len(good)] = V[sel]
+            W[m:m + len(good)] = W[sel]
+            rows = list(range(m)) + [m + j for j in good]
+            blk = blk[np.ix_(rows, good)]
+            added = len(good)
         T[:m + added, m:m + added] = blk
         T[m:m + added, :m + added] = blk.T
         m += added

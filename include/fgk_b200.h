@@ -257,6 +257,14 @@ int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* const* peer_ds
                     uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
                     uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
 
+/* Small all-reduce (sum) of n <= slot_stride doubles over peer memory: the dot products of a
+ * row-sharded Krylov iteration.  peer_scratch[p]: rank p's scratch, 2 * world * slot_stride doubles;
+ * area alternates 0 / 1 between consecutive calls.  Partials are added in rank order: identical
+ * bits on every rank.  src and dst may alias. */
+int fgk_peer_allreduce_sum(const double* src, int64_t n, double* dst, double* const* peer_scratch,
+                           int64_t slot_stride, int area, uint64_t* const* peer_flags, int rank, int world,
+                           uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
+
 /* One Taylor term of exp(t (H - mu I)) psi (scipy expm_multiply under skqd.py:291-293), complex128
  * vectors of length n: B <- c (y - mu B) with y = H B, F <- F + B; norms[0] = max |B_i|,
  * norms[1] = max |F_i| (device double[2], written by the call). */

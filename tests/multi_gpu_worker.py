@@ -80,6 +80,16 @@ def main():
         assert float((yh.to(dev) - yref[lo:hi]).abs().max()) < 1e-11
         yh = fop.matvec_host(x.cpu().pin_memory())          # twice: buffers ping-pong
         assert float((yh.to(dev) - yref[lo:hi]).abs().max()) < 1e-11
+        # small all-reduce over peer memory: identical bits on every rank, equals NCCL's sum
+        for rep in range(5):                                  # consecutive calls alternate the scratch area
+            part = torch.randn(37 + rep, dtype=torch.float64, generator=torch.Generator().manual_seed(100 * rank + rep)).to(dev)
+            ref_sum = part.clone()
+            dist.all_reduce(ref_sum)
+            got_sum = fop.allreduce_sum_(part.clone())
+            assert float((got_sum - ref_sum).abs().max()) < 1e-13
+            gathered = [torch.empty_like(got_sum) for _ in range(world)]
+            dist.all_gather(gathered, got_sum)
+            assert all(torch.equal(gathered[0], gq) for gq in gathered)
         # replicated Davidson through matvec, row-sharded Davidson through matvec_local
         wf, _ = lowest_eigenpairs(fop, k=1, matvec=fop.matvec, diagonal=fop.diagonal(), dense_max=0)
         ws, vs = lowest_eigenpairs(fop, k=2, sharded=fop)
@@ -142,7 +152,8 @@ def main():
     # step for exp(-i dt H_S), growth by the sharded MAXABS selection -- same sets, same amplitudes
     # and same energies as the single-process run
     cfg = fgk.SKQDConfig(max_krylov_dim=3, shots_per_krylov=4000, subspace_mode="adaptive",
-                         max_subspace_size=24000, expand_sources=48, expand_new_per_round=16000)
+                         max_subspace_size=4096 * wsz + 12000, expand_sources=48,
+                         expand_new_per_round=4096 * wsz + 4000)     # the set must pass 4096 rows per rank
     nf = H.unpack(dets[torch.randperm(n, generator=torch.Generator().manual_seed(4))[:300].to(dev)].contiguous())
     fgk.SampleBasedKrylovDiagonalization._world = staticmethod(lambda: wsz)
     torch.manual_seed(5)
@@ -168,4 +179,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        print("WORKER_FAILED rank", os.environ.get("RANK"), flush=True)
+        traceback.print_exc(file=sys.stdout)
+        sys.stdout.flush()
+        raise

@@ -19,5 +19,5 @@ def test_sharded_equals_single(world):
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
            os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.returncode == 0, out.stdout[-6000:] + out.stderr[-1500:]
     assert "MULTI_GPU_OK" in out.stdout

@@ -228,7 +228,7 @@ def test_projected_packed_direct_build(fgk, name):
             Pf = H.projected_operator(dets, mode, index=idx, packed=True, min_rows=1)
             assert not getattr(Pf, "sell_only", False) and getattr(Pf, "_sell", None) is not None
             continue
-        assert Pp.sell_only and Pp.count_pass == "exact"          # small basis: no sampling
+        assert Pp.sell_only
         _packed_equals_csr(Pp, Pc)
     if n > 40:
         lo, hi = n // 3, n - 5
@@ -239,9 +239,10 @@ def test_projected_packed_direct_build(fgk, name):
 
 
 def test_projected_packed_bound_and_sampling(fgk):
-    """CAS-window basis with dense integrals: the list-length bound is exact, the sampled count
-    confirms it and no count pass runs; a random sub-basis needs the exact count (pairs missing);
-    the eigenvalue through the packed operator equals the CSR one"""
+    """CAS-window (product) basis with dense integrals: the list-length bound is exact and no count
+    pass runs; a random sub-basis needs the exact count (pairs missing); a full space with symmetry
+    zeros is refilled with the lengths of its first fill; the eigenvalue through the packed operator
+    equals the CSR one"""
     from bench import synth_integrals, cas_window_basis
     h1, gg = synth_integrals(20, seed=2)
     H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, gg, 0.0, 10, 20, 5, 5), "cuda:0")
@@ -261,6 +262,17 @@ def test_projected_packed_bound_and_sampling(fgk):
     Ps = H.projected_packed(sub, fgk.H_RAW, packed=True)
     assert Ps.count_pass == "exact"
     _packed_equals_csr(Ps, H.projected_csr(sub, fgk.H_RAW, packed=True))
+    # product basis whose bound is NOT reached (real molecule: symmetry zeros): refilled, no padding read
+    gm = load_golden("ham_n2_sto3g")
+    Hm, _, _ = make_pair(fgk, gm)
+    full = Hm.fci_dets()
+    Pm = Hm.projected_packed(full, fgk.H_RAW, packed=True)
+    assert Pm.count_pass.startswith("the first fill")
+    _packed_equals_csr(Pm, Hm.projected_csr(full, fgk.H_RAW, packed=True))
+    w_ = (Pm._sellf[0][1:] - Pm._sellf[0][:-1]) // 32
+    lens_ = torch.zeros(w_.shape[0] * 32, dtype=torch.int64, device="cuda:0")
+    lens_[:full.shape[0]] = Pm._row_len.long()
+    assert torch.equal(w_, (lens_.view(-1, 32).max(dim=1).values + 1) // 2)
     # the fused multi-GPU operator takes the directly built storage as it is
     from flow_guided_krylov_b200 import dist as fd
     fop = fd.FusedShardedOperator(Pp)
