@@ -661,13 +661,14 @@ def _run_ours(args, out):
                 calls[0] += 1
                 return kop.matvec(v)
         else:
-            kop = None
+            from flow_guided_krylov_b200.solvers import _LocalOp
+            kop = _LocalOp(P)                    # one GPU: the same fused iteration, no exchange
             diag_full = P.diagonal()
 
             def kmv(v):
                 calls[0] += 1
                 return P.matvec(v)
-        sharded_dav = kop if isinstance(kop, fdist.FusedShardedOperator) else None
+        sharded_dav = kop if hasattr(kop, "matvec_local") and not isinstance(kop, fdist.ShardedOperator) else None
         if sharded_dav is not None:          # count the products of the row-sharded iteration
             _ml = kop.matvec_local
 
@@ -685,8 +686,9 @@ def _run_ours(args, out):
         res = kmv(vec[:, 0].contiguous()) - w[0] * vec[:, 0]
         krylov = {"davidson_seconds": t_dav, "davidson_matvecs": n_dav, "e0": float(w[0]),
                   "residual_norm": float(torch.linalg.norm(res)),
-                  "vectors": "row-sharded (peer gather per product, all-reduced dot products)" if sharded_dav is not None
-                             else "replicated",
+                  "vectors": ("row-sharded (peer gather per product, peer-memory all-reduce of the dot products), "
+                              "fused iteration kernels" if world > 1 else "fused iteration kernels (fgk_davidson_step)")
+                             if sharded_dav is not None else "replicated",
                   "storage": "packed SELL-32 (exact f32 off-diagonals)" if P._sellf is not None else "SELL-32 FP64"}
         if args.krylov_phases:      # second, instrumented solve (synchronises between phases)
             phs = {}
@@ -709,7 +711,7 @@ def _run_ours(args, out):
 
         def zmv(v):
             zc[0] += 1
-            return kop.matvec(v) if kop is not None else P.matvec(v)
+            return kop.matvec(v) if world > 1 else P.matvec(v)
         from flow_guided_krylov_b200.solvers import spectral_radius_estimate
         barrier()
         t0 = time.perf_counter()

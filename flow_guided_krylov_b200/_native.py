@@ -55,6 +55,7 @@ _SIGNATURES = {
     "fgk_sell_pack_f32": (ci, [i64, i64, vp, vp, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_sell_f32_f64": (ci, [i64, i64, vp, vp, vp, vp, vp, ci, vp]),
     "fgk_spmv_sell_f32_z": (ci, [i64, i64, vp, vp, vp, vp, vp, ci, vp]),
+    "fgk_davidson_step": (ci, [ci, i64, i64, ci, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, ci, vp, ci, vp]),
     "fgk_taylor_update_z": (ci, [i64, vp, vp, vp, dbl, dbl, dbl, vp, ci, vp]),
     "fgk_peer_alloc": (ci, [C.c_size_t, ci, C.POINTER(vp), C.c_char_p]),
     "fgk_peer_open": (ci, [C.c_char_p, ci, C.POINTER(vp)]),

@@ -16,6 +16,26 @@ import math
 import torch
 
 DENSE_EIG_MAX = 3072
+FUSED_DAVIDSON_MIN_ROWS = 16384     # above: fused iteration kernels (fgk_davidson_step) on one GPU too
+
+
+class _LocalOp:
+    """one-GPU adapter with the contract of dist.FusedShardedOperator (row-sharded drivers)"""
+
+    def __init__(self, P):
+        self.P, self.n, self.row_begin, self.row_end, self.world, self.rank = P, P.n, 0, P.n, 1, 0
+
+    def diagonal(self):
+        return self.P.diagonal()
+
+    def matvec_local(self, x, out=None):
+        return self.P.matvec(x, out=out)
+
+    def allreduce_sum_(self, t):
+        return t
+
+    def check(self):
+        pass
 
 
 def _full_matvec(P, x):
@@ -60,7 +80,9 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
     if dense_max is None:
         dense_max = DENSE_EIG_MAX                  # read at call time (tunable)
     if sharded is not None:
-        return _davidson_sharded(sharded, min(k, P.n), tol, max_iter, max_space, v0, phases)
+        fused = sharded.diagonal().is_cuda and (max_space is None or max_space <= 64)
+        drv = _davidson_fused if fused else _davidson_sharded
+        return drv(sharded, min(k, P.n), tol, max_iter, max_space, v0, phases)
     n = P.n
     mv = matvec if matvec is not None else (lambda x: _full_matvec(P, x))
     k = min(k, n)
@@ -70,6 +92,10 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         return w[:k].clone(), v[:, :k].clone()
     diag = diagonal if diagonal is not None else P.diagonal()
     dev = diag.device
+    if (matvec is None and dev.type == "cuda" and hasattr(P, "optimize_for_matvec") and n >= FUSED_DAVIDSON_MIN_ROWS
+            and (max_space is None or max_space <= 64)):
+        P.optimize_for_matvec()
+        return _davidson_fused(_LocalOp(P), k, tol, max_iter, max_space, v0, phases)
     ph = _Phases(phases, dev)
     ph.mark(None)
     if matvec is None and hasattr(P, "optimize_for_matvec"):
@@ -159,6 +185,144 @@ def lowest_eigenpairs(P, k=1, tol=1e-11, max_iter=2000, max_space=None, matvec=N
         m += added
         ph.mark("project")
     return w_out.clone(), X.T.contiguous()
+
+
+def _davidson_fused(op, k, tol, max_iter, max_space, v0, phases):
+    """The row-sharded block Davidson of _davidson_sharded with its vector algebra in four fused
+    kernels per correction (fgk_davidson_step: Ritz residual + correction + first projection;
+    orthogonalisation pass + second projection; normalised new vector; projection of H v) instead
+    of ~45 small tensor kernels, and the dot products summed by one peer-memory all-reduce launch
+    each.  Same iteration (start vectors, restart rule, lagged convergence test)."""
+    import ctypes as C
+    import numpy as np
+    from . import _native as nat
+    from .dist import allgather_vector
+    L = nat.lib()
+    n, lo, hi = op.n, op.row_begin, op.row_end
+    nl = hi - lo
+    diag_full = op.diagonal()
+    diag = diag_full[lo:hi].contiguous()
+    dev = diag.device
+    dev_i = nat.device_index(dev)
+    ph = _Phases(phases, dev)
+    ph.mark(None)
+    allsum = op.allreduce_sum_
+
+    nb = min(max(2 * k, k + 2), n)
+    m_max = min(n, max_space if max_space is not None else max(12 * k, 36))
+    m_max = min(max(m_max, nb + k), 64)
+    keep = min(max(2 * k + 2, m_max // 3), m_max - k)
+    V = torch.zeros(m_max, nl, dtype=torch.float64, device=dev)
+    W = torch.zeros(m_max, nl, dtype=torch.float64, device=dev)
+    start = torch.argsort(diag_full)[:nb]
+    V0 = torch.zeros(n, nb, dtype=torch.float64, device=dev)
+    V0[start, torch.arange(nb, device=dev)] = 1.0
+    gen = torch.Generator(device=dev).manual_seed(20240229)       # same stream on every rank
+    V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen, device=dev)
+    if v0 is not None:
+        V0[:, 0] = v0.to(dev, torch.float64)
+    V0 = V0[lo:hi].contiguous()
+    for _ in range(2):                                   # CholQR2 on the sharded block
+        G = allsum((V0.T @ V0).contiguous())
+        R = torch.linalg.cholesky(G, upper=True)
+        V0 = torch.linalg.solve_triangular(R, V0, upper=True, left=False)
+    m = nb
+    V[:m] = V0.T
+    del V0
+    for i in range(m):
+        op.matvec_local(V[i], out=W[i])
+    T = np.zeros((m_max, m_max))
+    T[:m, :m] = allsum((V[:m] @ W[:m].T).contiguous()).cpu().numpy()
+
+    props = torch.cuda.get_device_properties(dev)
+    G_ = max(1, min(2 * props.multi_processor_count, -(-nl // 256)))
+    partial = torch.empty(G_, m_max + 1, dtype=torch.float64, device=dev)
+    tvec = torch.empty(nl, dtype=torch.float64, device=dev)
+    st = nat.stream_ptr(dev)
+    HostCoef = C.c_double * 64
+
+    def step(mode, mm, host_coef=None, dev_coef=None, tt=None, theta=0.0, w=None, out=None, nrm=None):
+        nat.check(L.fgk_davidson_step(
+            mode, nl, nl, mm, nat.ptr(V), nat.ptr(W), host_coef, nat.ptr(dev_coef), nat.ptr(tt), float(theta),
+            nat.ptr(diag), nat.ptr(tvec), nat.ptr(w), nat.ptr(out), nat.ptr(partial), G_, nat.ptr(nrm), dev_i, st))
+
+    def reduced(mm):
+        """block partials -> one vector (rows added in order) -> sum over the ranks"""
+        return allsum(partial.view(-1)[: G_ * (mm + 1)].view(G_, mm + 1).sum(dim=0))
+
+    w_out = X = None
+    s_last = None
+    ph.mark("setup")
+    rn_prev = np.full(k, np.inf)
+    for _ in range(max_iter):
+        Tm = 0.5 * (T[:m, :m] + T[:m, :m].T)
+        th, s = np.linalg.eigh(Tm)
+        s_last, m_last = s, m
+        w_out = th[:k].copy()
+        scale = max(1.0, float(np.abs(th[:k]).max()))
+        todo = [i for i in range(k) if rn_prev[i] >= tol * scale]
+        if m + len(todo) > m_max:                   # thick restart: rotate V and H V together
+            q = keep
+            s_dev = torch.from_numpy(np.ascontiguousarray(s.T)).to(dev)
+            V[:q] = s_dev[:q] @ V[:m]
+            W[:q] = s_dev[:q] @ W[:m]
+            T[:] = 0.0
+            T[np.arange(q), np.arange(q)] = th[:q]
+            s = np.eye(q)                           # the kept Ritz vectors are the new basis
+            s_last, m_last = s, q
+            m = q
+        added = 0
+        norms, rrs = [], []
+        for i in todo:
+            mm = m + added
+            coef = np.zeros(64)
+            coef[:m] = s[:m, i]                     # Ritz vector i in the (rotated) basis; new rows get 0
+            step(0, mm, host_coef=HostCoef(*coef), theta=th[i])
+            v1 = reduced(mm)
+            rrs.append(v1[mm:mm + 1])
+            step(1, mm, dev_coef=v1)
+            v2 = reduced(mm)
+            nrm = torch.empty(1, dtype=torch.float64, device=dev)
+            step(2, mm, dev_coef=v2, tt=v2[mm:], out=V[mm], nrm=nrm)
+            norms.append(nrm)
+            added += 1
+        ph.mark("correction_orth")
+        for j in range(m, m + added):
+            op.matvec_local(V[j], out=W[j])
+        ph.mark("matvec")
+        cols = []
+        for j in range(m, m + added):
+            step(3, m + added, w=W[j])
+            cols.append(reduced(m + added)[: m + added])
+        back = torch.cat(cols + norms + rrs).cpu().numpy()       # ONE read-back per iteration
+        nbk = (m + added) * added
+        blk = back[:nbk].reshape(added, m + added).T
+        ok = back[nbk:nbk + added] > 1e-10
+        rn_new = np.sqrt(np.maximum(back[nbk + added:], 0.0))
+        for q_, i in enumerate(todo):
+            rn_prev[i] = rn_new[q_]
+        if rn_prev.max() < tol * scale:
+            break                                   # the Ritz pairs of this iteration are converged
+        if not ok.all():                            # drop vanished corrections (rare: breakdown)
+            good = [j for j in range(added) if ok[j]]
+            if not good:
+                break
+            sel = torch.tensor([m + j for j in good], device=dev)
+            V[m:m + len(good)] = V[sel]
+            W[m:m + len(good)] = W[sel]
+            rows = list(range(m)) + [m + j for j in good]
+            blk = blk[np.ix_(rows, good)]
+            added = len(good)
+        T[:m + added, m:m + added] = blk
+        T[m:m + added, :m + added] = blk.T
+        m += added
+        ph.mark("project")
+    op.check()
+    s_dev = torch.from_numpy(np.ascontiguousarray(s_last[:m_last, :k].T)).to(dev)
+    X = s_dev @ V[:m_last]
+    Xf = torch.stack([allgather_vector(X[i].contiguous(), n) for i in range(X.shape[0])], dim=1) if op.world > 1 \
+        else X.T.contiguous()
+    return torch.from_numpy(w_out).to(dev), Xf.contiguous()
 
 
 def _davidson_sharded(op, k, tol, max_iter, max_space, v0, phases):

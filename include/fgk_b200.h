@@ -257,6 +257,18 @@ int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* const* peer_ds
                     uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
                     uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
 
+/* Fused vector algebra of one block-Davidson iteration (replaces np.linalg.eigh / eigsh of
+ * residual_expansion.py:408-443, skqd.py:754-796 together with solvers.py).  V, W: the basis
+ * vectors and their images as rows (m_max x ld, ld >= n_local).  mode 0: t = (W^T s - theta V^T s)
+ * / (theta - diag) with s = host_coef[0..m), partial[cta][j] = V_j . t, partial[cta][m] = r . r;
+ * mode 1: t -= V^T c (c = dev_coef), partial = {V_j . t, t . t}; mode 2: out = (t - V^T c) /
+ * sqrt(*tt_dev - c . c), the norm to *nrm_out; mode 3: partial[cta][j] = V_j . w.  partial has
+ * n_blocks rows of m + 1 doubles (the caller adds the rows in order, then across ranks). */
+int fgk_davidson_step(int mode, int64_t n_local, int64_t ld, int m, const double* V, const double* W,
+                      const double* host_coef, const double* dev_coef, const double* tt_dev, double theta,
+                      const double* diag, double* t, const double* w, double* out, double* partial,
+                      int n_blocks, double* nrm_out, int device, void* stream);
+
 /* Small all-reduce (sum) of n <= slot_stride doubles over peer memory: the dot products of a
  * row-sharded Krylov iteration.  peer_scratch[p]: rank p's scratch, 2 * world * slot_stride doubles;
  * area alternates 0 / 1 between consecutive calls.  Partials are added in rank order: identical

@@ -944,6 +944,64 @@ def test_one_launch_peer_step_world_1(fgk):
         fop.close()
 
 
+def test_guard_bands_around_kernel_outputs(fgk):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02i_compute_sanitizer_closed.txt), so
+    the out-of-bounds check is our own: every buffer the lock-free PT2 upsert, the score / gather
+    pair and the packed row builder write is carved out of a larger allocation whose guard bands
+    (a fixed pattern before and after) must come back untouched -- under heavy contention (many
+    sources reaching the same candidates, a table forced into many bucket passes)."""
+    import ctypes as C
+    from flow_guided_krylov_b200 import _native as nat
+    from flow_guided_krylov_b200.expansion import Pt2Workspace, pt2_select
+    g = load_golden("sci_n2_sto3g")
+    H, O, n_orb = make_pair(fgk, g)
+    dets = H.pack(t64(g["basis0"]))
+    idx = fgk.BasisIndex(dets)
+    GUARD, PAT = 4096, 0x5A5A5A5A5A5A5A5A
+
+    def guarded(n_words):
+        big = torch.full((n_words + 2 * GUARD,), PAT, dtype=torch.int64, device="cuda:0")
+        return big, big[GUARD:GUARD + n_words]
+
+    def intact(big, n_words):
+        return bool((big[:GUARD] == PAT).all()) and bool((big[GUARD + n_words:] == PAT).all())
+
+    cap = 3000                                            # far fewer than the ~1e5 distinct candidates
+    slots = 8192
+    ws = Pt2Workspace.__new__(Pt2Workspace)
+    ws.capacity, ws.device, ws.queue_pairs = cap, "cuda:0", 0
+    bt, ws._table = guarded(slots)
+    bp, pool = guarded(4 * cap)
+    ws._pool = pool.view(cap, 4)
+    bc, ws._counters = guarded(4)
+    ws._counters.zero_()
+    h = C.c_void_p()
+    nat.check(nat.lib().fgk_pt2_create(cap, slots, nat.ptr(ws._table), nat.ptr(ws._pool), nat.ptr(ws._counters), 0, C.byref(h)))
+    ws._h = h
+    ws.reset()
+    v = torch.from_numpy(g["r0_v"]).cuda()
+    sel, imp, st = pt2_select(H, idx, v, float(g["r0_E"]), 100, workspace=ws)
+    ref_sel, ref_imp, _ = pt2_select(H, idx, v, float(g["r0_E"]), 100)
+    assert st["passes"] > 8 and torch.equal(sel, ref_sel) and torch.equal(imp, ref_imp)
+    assert intact(bt, slots) and intact(bp, 4 * cap) and intact(bc, 4)
+    # packed row builder: units and row lengths
+    full = H.fci_dets()
+    idxf = fgk.BasisIndex(full)
+    P = H.projected_packed(full, fgk.H_RAW, index=idxf, packed=True)
+    sp = P._sellf[0]
+    total = int(sp[-1])
+    bpk, pk = guarded(2 * total)                          # 16-byte units = 2 int64 words
+    brl, rl = guarded((full.shape[0] + 1) // 2)           # int32 row lengths
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    nat.check(nat.lib().fgk_projh_packed_fill(H._h, idxf._h, idxf.string_lists(H), 0, full.shape[0], fgk.H_RAW,
+                                              nat.ptr(sp, torch.int64), nat.ptr(pk), nat.ptr(rl), nat.ptr(flag, torch.int32),
+                                              nat.stream_ptr("cuda:0")))
+    torch.cuda.synchronize()
+    assert int(flag) == 0
+    assert intact(bpk, 2 * total) and intact(brl, (full.shape[0] + 1) // 2)
+    assert torch.equal(pk.view(torch.int32).view(-1, 4), P._sellf[1][:total])
+
+
 def test_pt2_select_head_equals_full_topk(fgk):
     """fgk_pt2_score / fgk_pt2_gather (score in place, exponent histogram, gather the head) followed
     by the deterministic top-k must pick exactly what the top-k over the full export picks: for
