@@ -669,6 +669,7 @@ def _run_ours(args, out):
                 calls[0] += 1
                 return P.matvec(v)
         sharded_dav = kop if hasattr(kop, "matvec_local") and not isinstance(kop, fdist.ShardedOperator) else None
+        counted = _ml = None
         if sharded_dav is not None:          # count the products of the row-sharded iteration
             _ml = kop.matvec_local
 
@@ -737,7 +738,7 @@ def _run_ours(args, out):
         if kop is not None and hasattr(kop, "close"):
             kop.close()
         kop = sharded_dav = None          # they hold the operator (tens of GB): release before the PT2 legs
-        kmv = zmv = None
+        kmv = zmv = counted = _ml = None
 
     # ---- PT2 sweep (candidates/s), same Hamiltonian and basis -------------------------
     pt2 = None

@@ -499,19 +499,24 @@ extern "C" int fgk_taylor_update_z(int64_t n, const double* y, double* B, double
 // ======================================================================================
 struct DavCoef { double c[64]; };
 
+// One lane = one row of the tile; the lane keeps its m basis entries V[j][i] in registers, so V is
+// read ONCE per pass (the projection needs them twice); every dot product is a warp shuffle
+// reduction accumulated per warp in shared memory.  64 independent 8-byte loads per lane keep the
+// memory system busy at 12 resident warps per SM.
 template <int MCAP, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restrict__ W,
       const __grid_constant__ DavCoef host_coef, const double* __restrict__ dev_coef, const double* __restrict__ tt_dev,
       double theta, const double* __restrict__ diag, double* __restrict__ t, const double* __restrict__ w,
       double* __restrict__ out, double* __restrict__ partial, double* nrm_out)
 {
     __shared__ double s_c[MCAP];
-    __shared__ double s_red[8][MCAP + 1];
+    __shared__ double s_acc[4][MCAP + 1];
     __shared__ double s_scale;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x < MCAP)
         s_c[threadIdx.x] = threadIdx.x < m ? (MODE == 0 ? host_coef.c[threadIdx.x] : (MODE == 3 ? 0.0 : dev_coef[threadIdx.x])) : 0.0;
+    for (int j = threadIdx.x; j < 4 * (MCAP + 1); j += blockDim.x) (&s_acc[0][0])[j] = 0.0;
     __syncthreads();
     if (MODE == 2) {
         if (threadIdx.x == 0) {
@@ -524,58 +529,61 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
         }
         __syncthreads();
     }
-    double acc[MCAP];
-#pragma unroll
-    for (int j = 0; j < MCAP; j++) acc[j] = 0.0;
     double extra = 0.0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (i64)gridDim.x * blockDim.x) {
-        double ti;
+    const i64 n_tiles = (nl + 31) >> 5;
+    for (i64 tile = (i64)blockIdx.x * 4 + wid; tile < n_tiles; tile += (i64)gridDim.x * 4) {
+        const i64 i = tile * 32 + lane;
+        const bool live = i < nl;
+        double v[MCAP];
+#pragma unroll
+        for (int j = 0; j < MCAP; j++) v[j] = (j < m && live) ? V[j * ld + i] : 0.0;
+        double ti = 0.0;
         if (MODE == 0) {
             double xs = 0.0, ws = 0.0;
 #pragma unroll
             for (int j = 0; j < MCAP; j++)
-                if (j < m) { xs = fma(s_c[j], V[j * ld + i], xs); ws = fma(s_c[j], W[j * ld + i], ws); }
-            const double r = ws - theta * xs;
-            double den = theta - diag[i];
-            if (fabs(den) < 1e-8) den = -1e-8;
-            ti = r / den;
-            extra = fma(r, r, extra);
-            t[i] = ti;
+                if (j < m) { xs = fma(s_c[j], v[j], xs); ws = fma(s_c[j], live ? W[j * ld + i] : 0.0, ws); }
+            if (live) {
+                const double r = ws - theta * xs;
+                double den = theta - diag[i];
+                if (fabs(den) < 1e-8) den = -1e-8;
+                ti = r / den;
+                extra = fma(r, r, extra);
+                t[i] = ti;
+            }
         } else if (MODE == 1 || MODE == 2) {
             double pr = 0.0;
 #pragma unroll
             for (int j = 0; j < MCAP; j++)
-                if (j < m) pr = fma(s_c[j], V[j * ld + i], pr);
-            ti = t[i] - pr;
-            if (MODE == 1) { extra = fma(ti, ti, extra); t[i] = ti; }
-            else out[i] = ti * s_scale;
-        } else {
+                if (j < m) pr = fma(s_c[j], v[j], pr);
+            if (live) {
+                ti = t[i] - pr;
+                if (MODE == 1) { extra = fma(ti, ti, extra); t[i] = ti; }
+                else out[i] = ti * s_scale;
+            }
+        } else if (live) {
             ti = w[i];
         }
         if (MODE != 2) {
 #pragma unroll
-            for (int j = 0; j < MCAP; j++)
-                if (j < m) acc[j] = fma(V[j * ld + i], ti, acc[j]);
+            for (int j = 0; j < MCAP; j++) {
+                if (j < m) {                                   // warp-uniform
+                    double p = v[j] * ti;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+                    if (lane == 0) s_acc[wid][j] += p;
+                }
+            }
         }
     }
     if (MODE == 2) return;
 #pragma unroll
-    for (int j = 0; j < MCAP; j++) {
-        double v = acc[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[wid][j] = v;
-    }
-#pragma unroll
     for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
-    if (lane == 0) s_red[wid][MCAP] = extra;
+    if (lane == 0) s_acc[wid][MCAP] = extra;
     __syncthreads();
     if (threadIdx.x <= m) {
         const int j = threadIdx.x == m ? MCAP : threadIdx.x;
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) v += s_red[q][j];
-        partial[(i64)blockIdx.x * (m + 1) + threadIdx.x] = v;
+        partial[(i64)blockIdx.x * (m + 1) + threadIdx.x] = s_acc[0][j] + s_acc[1][j] + s_acc[2][j] + s_acc[3][j];
     }
 }
 
@@ -585,10 +593,10 @@ static void launch_dav(int mode, int grid, cudaStream_t st, i64 nl, i64 ld, int 
                        double* t, const double* w, double* out, double* partial, double* nrm)
 {
     switch (mode) {
-    case 0: k_dav<MCAP, 0><<<grid, 256, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
-    case 1: k_dav<MCAP, 1><<<grid, 256, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
-    case 2: k_dav<MCAP, 2><<<grid, 256, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
-    default: k_dav<MCAP, 3><<<grid, 256, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
+    case 0: k_dav<MCAP, 0><<<grid, 128, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
+    case 1: k_dav<MCAP, 1><<<grid, 128, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
+    case 2: k_dav<MCAP, 2><<<grid, 128, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
+    default: k_dav<MCAP, 3><<<grid, 128, 0, st>>>(nl, ld, m, V, W, hc, dc, tt, theta, diag, t, w, out, partial, nrm); break;
     }
 }
 

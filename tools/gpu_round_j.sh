@@ -1,0 +1,2 @@
+python -m pytest tests -m gpu -x -q -rs > gpurun_out/r02j_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02j_pytest.log
+python bench.py --steps 20 --warmup 3 --krylov-phases > gpurun_out/r02j_bench.json 2> gpurun_out/r02j_bench.err; echo "bench exit $?" >> gpurun_out/r02j_bench.err
