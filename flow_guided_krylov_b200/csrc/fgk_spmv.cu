@@ -594,7 +594,7 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
         }
     }
     if (MODE == 2) return;
-    s_acc[wid][lane] = acc0;
+    if (lane < MCAP) s_acc[wid][lane] = acc0;
     if (MCAP > 32) s_acc[wid][lane + 32] = acc1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
