@@ -61,7 +61,6 @@ _SIGNATURES = {
     "fgk_peer_open": (ci, [C.c_char_p, ci, C.POINTER(vp)]),
     "fgk_peer_close": (ci, [vp, ci]),
     "fgk_peer_free": (ci, [vp, ci]),
-    "fgk_spmv_sell_f64_allgather": (ci, [i64, vp, vp, vp, vp, C.POINTER(vp), ci, i64, ci, vp]),
     "fgk_peer_barrier": (ci, [C.POINTER(vp), ci, ci, C.c_uint64, vp, ci, vp]),
     "fgk_peer_step": (ci, [i64, vp, vp, vp, vp, vp, C.POINTER(vp), ci, i64, C.POINTER(vp), ci, ci, C.c_uint64,
                            vp, vp, ci, vp]),

@@ -218,19 +218,16 @@ int fgk_spmv_sell_f32_z(int64_t n_rows, int64_t row_offset, const int64_t* slice
 /* ---- multi-GPU H.v with the all-gather fused into the product (one process per GPU) ----
  * fgk_peer_alloc: cudaMalloc'ed, zeroed buffer + its 64-byte cudaIpc handle (exchange the
  * handles with any host-side collective); fgk_peer_open maps a peer's buffer into this
- * process.  fgk_spmv_sell_f64_allgather computes this rank's rows of y = H x and stores
- * y_r to peer_out[p][row_offset + r] for every rank p (peer_out: HOST array of `world`
- * device pointers, own buffer included; x must be a different buffer).
- * fgk_peer_barrier: flag barrier over peer-mapped arrays (peer_flags[p] = rank p's
- * uint64[world] array); epoch must increase by one per call; *err_flag (device) is set to
- * the epoch if a peer never arrives (bounded spin). */
+ * process.  Peer pointer arguments (peer_out, peer_flags, ...) are HOST arrays of `world`
+ * device pointers, the rank's own buffer included.
+ * fgk_peer_barrier: stand-alone flag barrier over peer-mapped arrays (peer_flags[p] = rank p's
+ * uint64[world] array); epoch must increase by one per synchronising call (fgk_peer_barrier /
+ * _step / _gather / _allreduce_sum share the flags); *err_flag (device) is set to the epoch if a
+ * peer never arrives (bounded spin). */
 int fgk_peer_alloc(size_t bytes, int device, void** dev_ptr, unsigned char* handle64);
 int fgk_peer_open(const unsigned char* handle64, int device, void** dev_ptr);
 int fgk_peer_close(void* dev_ptr, int device);
 int fgk_peer_free(void* dev_ptr, int device);
-int fgk_spmv_sell_f64_allgather(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
-                                const double* sell_vals, const double* x, double* const* peer_out,
-                                int world, int64_t row_offset, int device, void* stream);
 int fgk_peer_barrier(uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
                      uint64_t* err_flag, int device, void* stream);
 
