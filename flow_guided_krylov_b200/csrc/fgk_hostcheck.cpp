@@ -426,9 +426,11 @@ long hc_bra_row4(void* h, const u64* basis, long n, long i, int mode, int* out_c
         return it == pair.end() ? -1 : it->second;
     };
     auto one = [&](float vij, float vji, long j) {
+        float f;
         double v;
-        if (j >= 0 && entry_value(sym, drop0, vij, vji, v)) {
-            if (m < cap) { out_cols[m] = (int)j; out_vals[m] = v; }
+        bool exact;
+        if (j >= 0 && entry_value_f32(sym, drop0, vij, vji, f, v, exact)) {     // the kernel's decision function
+            if (m < cap) { out_cols[m] = (int)j; out_vals[m] = exact ? (double)f : v; }
             m++;
         }
     };

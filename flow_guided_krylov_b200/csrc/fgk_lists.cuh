@@ -74,6 +74,28 @@ FGK_HD bool entry_value(bool sym, bool drop0, float vij, float vji, double& v)
     return !(drop0 && v == 0.0);
 }
 
+// the same decision with the value as the float32 number the packed operator stores: when both
+// directions agree (symmetric integrals: always, except the F3 sign cancellations) the average IS
+// that float32 number and no FP64 arithmetic is needed; `exact` = false if 0.5 (vij + vji) is not
+// a float32 number (v then carries the FP64 value)
+FGK_HD bool entry_value_f32(bool sym, bool drop0, float vij, float vji, float& f, double& v, bool& exact)
+{
+    const bool kij = (vij < 0.f ? -vij : vij) > 1e-12f;
+    const bool kji = sym && (vji < 0.f ? -vji : vji) > 1e-12f;
+    if (!kij && !kji) return false;
+    const float a = kij ? vij : 0.f, b = kji ? vji : 0.f;
+    exact = true;
+    if (!sym || a == b) {
+        f = a;
+        v = (double)a;
+    } else {
+        v = 0.5 * ((double)a + (double)b);
+        f = (float)v;
+        exact = (double)f == v;
+    }
+    return !(drop0 && v == 0.0);
+}
+
 // alpha-beta double built from one alpha single and one beta single (molecular.py:302-318)
 template <class Ld>
 FGK_HD void ab_values(const HamView& H, const LEntry& ea, const LEntry& eb, bool sym, Ld ldf, float& vij, float& vji)

@@ -133,15 +133,17 @@ def merge_topk(dets: torch.Tensor, score: torch.Tensor, k: int, n_orb: int, grou
     if ws == 1:
         return ld, ls
     m = ld.shape[0]
-    pd = torch.zeros(k, 2, dtype=torch.int64, device=dets.device)
+    # one collective: rows {alpha, beta, score bits}; padding rows carry -inf
+    pk = torch.zeros(k, 3, dtype=torch.int64, device=dets.device)
     ps = torch.full((k,), float("-inf"), dtype=torch.float64, device=dets.device)
-    pd[:m], ps[:m] = ld, ls.to(torch.float64)
-    gd = torch.empty(ws * k, 2, dtype=torch.int64, device=dets.device)
-    gs = torch.empty(ws * k, dtype=torch.float64, device=dets.device)
-    dist.all_gather_into_tensor(gd, pd, group=group)
-    dist.all_gather_into_tensor(gs, ps, group=group)
+    ps[:m] = ls.to(torch.float64)
+    pk[:m, :2] = ld
+    pk[:, 2] = ps.view(torch.int64)
+    gk = torch.empty(ws * k, 3, dtype=torch.int64, device=dets.device)
+    dist.all_gather_into_tensor(gk, pk, group=group)
+    gs = gk[:, 2].contiguous().view(torch.float64)
     live = gs > float("-inf")
-    return select_top_k(gd[live], gs[live], k, n_orb)
+    return select_top_k(gk[live][:, :2].contiguous(), gs[live], k, n_orb)
 
 
 def allreduce_scalar(x: float, op="sum", device="cpu") -> float:
@@ -208,22 +210,27 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
         return empty + (dict(n_sources=0, raw_candidates=0, passes=1, raw_candidates_total=0, unique_total=0),)
     wa = workspace if workspace is not None else default_pt2_workspace(ham, -(-n_src // ws))
     # every rank must run the same number of bucket passes: size them for the smallest workspace
-    cap = int(-allreduce_scalar(-float(wa.capacity), "max", dev))
+    # (agreed once per workspace object: two small collectives less on every later sweep)
+    shared = getattr(wa, "_shared_sizes", None)
+    if shared is None or shared[0] != ws:
+        t = torch.tensor([-float(wa.capacity), -float(wa.queue_pairs)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        shared = wa._shared_sizes = (ws, int(-t[0]), int(-t[1]))
+    _, cap, qp = shared
     raw_ub = n_src * _raw_connections_per_det(ham)
     local_passes = planned_passes(raw_ub, cap, ws)
-    qp = int(-allreduce_scalar(-float(wa.queue_pairs), "max", dev))
     if qp:
         local_passes = max(local_passes, -(-raw_ub // (qp * ws)))
     while True:
-        keep_d, keep_s, raw, uniq, ok = [], [], 0, 0, True
+        keep_d, keep_s, raw, uniq, over = [], [], 0, 0, False
         n_pass = ws * local_passes
         for p in range(local_passes):
             wa.reset()
             wa.accumulate(ham, index, src, cj, mode, n_pass, rank + ws * p)
             ns, nr, ov = wa.count()
-            if allreduce_scalar(1.0 if ov else 0.0, "max", dev) > 0:
-                ok = False
-                break
+            if ov:                      # this rank's pass overflowed: finish the loop cheaply, redo below
+                over = True
+                continue
             raw += nr
             d, sc, live = wa.select_head(ham if mode == nat.PT2_SUM else None, ns, energy, k)
             uniq += live
@@ -231,15 +238,20 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
             keep_d.append(sd.clone())
             keep_s.append(ss.clone())
             del d, sc
-        if ok:
+        # ONE collective per sweep: overflow flag (max) and the counters (sum) travel together
+        t = torch.tensor([1.0 if over else 0.0, float(raw), float(uniq)], dtype=torch.float64, device=dev)
+        tl = [torch.empty_like(t) for _ in range(ws)]
+        dist.all_gather(tl, t)
+        tot = torch.stack(tl).cpu()
+        if float(tot[:, 0].max()) == 0.0:
             break
         local_passes *= 2
         if ws * local_passes > max_passes:
             raise RuntimeError(f"PT2 candidate set does not fit the workspaces in {max_passes} passes")
     sel, sc = merge_topk(torch.cat(keep_d), torch.cat(keep_s), k, ham.n_orbitals)
     st = dict(n_sources=n_src, raw_candidates=raw, passes=local_passes, unique_local=uniq)
-    st["raw_candidates_total"] = int(allreduce_scalar(float(raw), "sum", dev))
-    st["unique_total"] = int(allreduce_scalar(float(uniq), "sum", dev))
+    st["raw_candidates_total"] = int(tot[:, 1].sum())
+    st["unique_total"] = int(tot[:, 2].sum())
     return sel, sc, st
 
 
