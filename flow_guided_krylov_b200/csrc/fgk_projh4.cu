@@ -172,7 +172,7 @@ extern "C" int fgk_strlists_info(fgk_strlists_t L, int64_t* n_single_a, int64_t*
 // MODE 1: exact off-diagonal row length (same walk, no stores); slices s = 0, stride, 2 stride, ...
 // MODE 2: fill the packed SELL-32 units + actual row lengths
 template <int MODE, bool DENSE>
-__global__ void __launch_bounds__(256, 5)      // 48 registers, no spills: 40 resident warps per SM (ncu r02l: 54 regs, 47 % warps active)
+__global__ void __launch_bounds__(256, 4)
 k_projh4(HamView H, IndexView I, StrListView LA, StrListView LB, const u64* __restrict__ alist,
          const u64* __restrict__ blist, i64 row_begin, i64 row_end, int mode, i64 slice_stride,
          i64* __restrict__ counts, const i64* __restrict__ slice_ptr, uint4* __restrict__ packed,
@@ -252,18 +252,45 @@ k_projh4(HamView H, IndexView I, StrListView LA, StrListView LB, const u64* __re
         // alpha-beta doubles: beta single outside (differs per lane), alpha single inside (neighbouring
         // rows share their alpha string: the inner loads are warp-wide broadcasts)
         const int mb = __reduce_max_sync(0xffffffffu, nsb), ma = __reduce_max_sync(0xffffffffu, nsa);
+        const int n2 = H.n_orb * H.n_orb;
         for (int kb = 0; kb < mb; kb++) {
+            const bool vb = kb < nsb;
             LEntry eb;
             eb.rank = 0; eb.vij = eb.vji = 0.f; eb.info = 0u;
-            if (kb < nsb) eb = LB.singles[sb0 + kb];
-            for (int ka = 0; ka < ma; ka++) {
-                if (kb < nsb && ka < nsa) {
-                    const LEntry ea = LA.singles[sa0 + ka];
-                    const int j = column(ea.rank, eb.rank);
-                    if (j >= 0) {
-                        float vij, vji;
-                        ab_values(H, ea, eb, sym, ldf, vij, vji);
-                        value(j, vij, vji);
+            if (vb) eb = LB.singles[sb0 + kb];
+            const float* const g_b = H.g + ((eb.info >> 12) & 0xfffu);     // bra-side column of g
+            const float* const g_k = H.g + (eb.info & 0xfffu);            // ket-side column
+            // four alpha singles per round: their pair-table and integral loads are all issued before
+            // the first result is used (ncu r02l: 45 % of the stall samples sat on the dependent
+            // pair -> g load chain of the one-at-a-time loop); the integral loads do not depend on
+            // the pair lookup, so they are unconditional (offsets of a zeroed entry are valid)
+            for (int ka0 = 0; ka0 < ma; ka0 += 4) {
+                unsigned info[4];
+                int j[4];
+                float rb[4], rk[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int ka = ka0 + u;
+                    info[u] = 0u;
+                    j[u] = -1;
+                    if (vb && ka < nsa) {
+                        const LEntry ea = LA.singles[sa0 + ka];
+                        info[u] = ea.info;
+                        j[u] = column(ea.rank, eb.rank);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    rb[u] = __ldg(g_b + (size_t)((info[u] >> 12) & 0xfffu) * n2);
+                    rk[u] = sym ? __ldg(g_k + (size_t)(info[u] & 0xfffu) * n2) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j[u] >= 0) {
+                        const unsigned px = info[u] ^ eb.info;
+                        const float vij = (((px >> 25) ^ 1u) & 1u) ? -rb[u] : rb[u];      // parity (bra side) = pb_a ^ pb_b ^ 1
+                        const float vji = (((px >> 24) ^ 1u) & 1u) ? -rk[u] : rk[u];      // parity (ket side) = pk_a ^ pk_b ^ 1
+                        value(j[u], vij, vji);
                     }
                 }
             }
