@@ -183,7 +183,6 @@ k_projh4(HamView H, IndexView I, StrListView LA, StrListView LB, const u64* __re
     const i64 rows = row_end - row_begin, n_slices = (rows + 31) >> 5;
     const bool sym = (mode & FGK_H_SYM) != 0, drop0 = (mode & FGK_H_DROP_ZEROS) != 0;
     const int nbs = (int)I.n_bstr;
-    LdgF ldf;
     bool bad = false;
     for (i64 s = warp0 * slice_stride; s < n_slices; s += nwarps * slice_stride) {
         const i64 rl = s * 32 + lane, i = row_begin + rl;
@@ -235,20 +234,32 @@ k_projh4(HamView H, IndexView I, StrListView LA, StrListView LB, const u64* __re
                 emit(j, f);
             }
         };
-        auto one = [&](const LEntry& e, int j) { value(j, e.vij, e.vji); };
-        // singles and same-spin doubles: the other spin keeps its own string
-        int m = __reduce_max_sync(0xffffffffu, nsa);
-        for (int k = 0; k < m; k++)
-            if (k < nsa) { const LEntry e = LA.singles[sa0 + k]; one(e, column(e.rank, ib)); }
-        m = __reduce_max_sync(0xffffffffu, nsb);
-        for (int k = 0; k < m; k++)
-            if (k < nsb) { const LEntry e = LB.singles[sb0 + k]; one(e, column(ia, e.rank)); }
-        m = __reduce_max_sync(0xffffffffu, nda);
-        for (int k = 0; k < m; k++)
-            if (k < nda) { const LEntry e = LA.doubles[da0 + k]; one(e, column(e.rank, ib)); }
-        m = __reduce_max_sync(0xffffffffu, ndb);
-        for (int k = 0; k < m; k++)
-            if (k < ndb) { const LEntry e = LB.doubles[db0 + k]; one(e, column(ia, e.rank)); }
+        // singles and same-spin doubles: the other spin keeps its own string.  Four list entries per
+        // round, their pair-table loads in flight together.
+        auto run_list = [&](const LEntry* __restrict__ list, i64 base0, int len, bool alpha_side) {
+            const int mlen = __reduce_max_sync(0xffffffffu, len);
+            for (int k0 = 0; k0 < mlen; k0 += 4) {
+                float vij[4], vji[4];
+                int j[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    j[u] = -1;
+                    vij[u] = vji[u] = 0.f;
+                    if (k0 + u < len) {
+                        const LEntry e = list[base0 + k0 + u];
+                        vij[u] = e.vij;
+                        vji[u] = e.vji;
+                        j[u] = alpha_side ? column(e.rank, ib) : column(ia, e.rank);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) value(j[u], vij[u], vji[u]);
+            }
+        };
+        run_list(LA.singles, sa0, nsa, true);
+        run_list(LB.singles, sb0, nsb, false);
+        run_list(LA.doubles, da0, nda, true);
+        run_list(LB.doubles, db0, ndb, false);
         // alpha-beta doubles: beta single outside (differs per lane), alpha single inside (neighbouring
         // rows share their alpha string: the inner loads are warp-wide broadcasts)
         const int mb = __reduce_max_sync(0xffffffffu, nsb), ma = __reduce_max_sync(0xffffffffu, nsa);

@@ -8,5 +8,8 @@ dev = "cuda:0"
 h1, g = synth_integrals(32, 0)
 H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, g, 0.0, 16, 32, 8, 8), dev)
 dets = torch.from_numpy(cas_window_basis(32, 4, 14, 4).view(np.int64)).to(dev)
-P = H.projected_packed(dets, fgk.H_SYM, packed=True, profile=True)
-print("ok", P.nnz, P.build_profile)
+idx = fgk.BasisIndex(dets)
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
+    P = H.projected_packed(dets, fgk.H_SYM, index=idx, packed=True, profile=True)
+    print("ok", P.nnz, P.build_profile, flush=True)
+    del P
