@@ -499,11 +499,13 @@ extern "C" int fgk_taylor_update_z(int64_t n, const double* y, double* B, double
 // ======================================================================================
 struct DavCoef { double c[64]; };
 
-// One lane = one row of the tile; the lane keeps its m basis entries V[j][i] in registers, so V is
-// read ONCE per pass (the projection needs them twice).  The m dot products of a tile are reduced
-// by a transpose through shared memory: lane l writes its m products, lane j then adds the 32
-// products of basis vector j (and j + 32) into a private accumulator -- ~4x fewer instructions than
-// m shuffle reductions (ncu r02k: the shuffle form was issue-bound at 2.1 TB/s).
+// One lane = one row of a 32-row tile.  Pass A streams the tile's m basis entries (and, for the
+// Ritz mode, the m entries of W) with eight independent loads in flight per lane and forms the
+// new vector entry; pass B reads the same V entries again -- they are in L1 / L2, the warp has
+// just loaded them -- and reduces the m dot products by a transpose through shared memory (lane l
+// writes its m products, lane j adds the 32 products of basis vector j and j + 32).  No
+// per-thread copy of the tile: ~60 registers instead of 187 (ncu r02k: the register-tile form
+// ran its Ritz mode at 1.06 TB/s with 8 resident warps per SM).
 template <int MCAP, int MODE>
 __global__ void __launch_bounds__(128)
 k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restrict__ W,
@@ -537,21 +539,15 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
     for (i64 tile = (i64)blockIdx.x * 4 + wid; tile < n_tiles; tile += (i64)gridDim.x * 4) {
         const i64 i = tile * 32 + lane;
         const bool live = i < nl;
-        double ws = 0.0;
-        if (MODE == 0) {                               // W is only streamed: its sum first, independent loads
-#pragma unroll
-            for (int j = 0; j < MCAP; j++)
-                if (j < m) ws = fma(s_c[j], live ? __ldg(W + j * ld + i) : 0.0, ws);
-        }
-        double v[MCAP];
-#pragma unroll
-        for (int j = 0; j < MCAP; j++) v[j] = (j < m && live) ? __ldg(V + j * ld + i) : 0.0;
+        const i64 ii = live ? i : nl - 1;              // dead lanes read a valid row and contribute nothing
         double ti = 0.0;
         if (MODE == 0) {
-            double xs = 0.0;
-#pragma unroll
-            for (int j = 0; j < MCAP; j++)
-                if (j < m) xs = fma(s_c[j], v[j], xs);
+            double xs = 0.0, ws = 0.0;
+#pragma unroll 8
+            for (int j = 0; j < m; j++) {
+                xs = fma(s_c[j], __ldg(V + j * ld + ii), xs);
+                ws = fma(s_c[j], __ldg(W + j * ld + ii), ws);
+            }
             if (live) {
                 const double r = ws - theta * xs;
                 double den = theta - diag[i];
@@ -562,9 +558,8 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
             }
         } else if (MODE == 1 || MODE == 2) {
             double pr = 0.0;
-#pragma unroll
-            for (int j = 0; j < MCAP; j++)
-                if (j < m) pr = fma(s_c[j], v[j], pr);
+#pragma unroll 8
+            for (int j = 0; j < m; j++) pr = fma(s_c[j], __ldg(V + j * ld + ii), pr);
             if (live) {
                 ti = t[i] - pr;
                 if (MODE == 1) { extra = fma(ti, ti, extra); t[i] = ti; }
@@ -574,9 +569,8 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
             ti = w[i];
         }
         if (MODE != 2) {
-#pragma unroll
-            for (int j = 0; j < MCAP; j++)
-                if (j < m) tile_s[j * 33 + lane] = v[j] * ti;
+#pragma unroll 8
+            for (int j = 0; j < m; j++) tile_s[j * 33 + lane] = __ldg(V + j * ld + ii) * ti;
             __syncwarp();
             if (lane < m) {
                 double a = 0.0;

@@ -235,7 +235,7 @@ def _davidson_fused(op, k, tol, max_iter, max_space, v0, phases):
     T[:m, :m] = allsum((V[:m] @ W[:m].T).contiguous()).cpu().numpy()
 
     props = torch.cuda.get_device_properties(dev)
-    G_ = max(1, min(4 * props.multi_processor_count, -(-nl // 128)))      # CTAs of 4 warps, one 32-row tile per warp step
+    G_ = max(1, min(6 * props.multi_processor_count, -(-nl // 128)))      # CTAs of 4 warps, one 32-row tile per warp step
     partial = torch.empty(G_, m_max + 1, dtype=torch.float64, device=dev)
     tvec = torch.empty(nl, dtype=torch.float64, device=dev)
     st = nat.stream_ptr(dev)
