@@ -499,13 +499,12 @@ extern "C" int fgk_taylor_update_z(int64_t n, const double* y, double* B, double
 // ======================================================================================
 struct DavCoef { double c[64]; };
 
-// One lane = one row of a 32-row tile.  Pass A streams the tile's m basis entries (and, for the
-// Ritz mode, the m entries of W) with eight independent loads in flight per lane and forms the
-// new vector entry; pass B reads the same V entries again -- they are in L1 / L2, the warp has
-// just loaded them -- and reduces the m dot products by a transpose through shared memory (lane l
-// writes its m products, lane j adds the 32 products of basis vector j and j + 32).  No
-// per-thread copy of the tile: ~60 registers instead of 187 (ncu r02k: the register-tile form
-// ran its Ritz mode at 1.06 TB/s with 8 resident warps per SM).
+// One lane = one row of a 32-row tile.  The m dot products of a tile are reduced by a transpose
+// through shared memory: lane l writes its m products, lane j adds the 32 products of basis
+// vector j (and j + 32).  Modes 1-3 keep the tile's V entries in registers (one read, all loads
+// in flight: 34-57 us per pass at 2.7-4.5 TB/s, ncu r02k); the Ritz mode reads V and W and would
+// need 187 registers that way (8 warps per SM, 1.06 TB/s), so it streams both and re-reads V
+// from cache (92 us).
 template <int MCAP, int MODE>
 __global__ void __launch_bounds__(128)
 k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restrict__ W,
@@ -542,8 +541,10 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
         const i64 ii = live ? i : nl - 1;              // dead lanes read a valid row and contribute nothing
         double ti = 0.0;
         if (MODE == 0) {
+            // Ritz mode: V and W are streamed (16 + 16 loads in flight), V is read again for the
+            // products below (L1 / L2: the warp has just loaded these lines)
             double xs = 0.0, ws = 0.0;
-#pragma unroll 8
+#pragma unroll 16
             for (int j = 0; j < m; j++) {
                 xs = fma(s_c[j], __ldg(V + j * ld + ii), xs);
                 ws = fma(s_c[j], __ldg(W + j * ld + ii), ws);
@@ -556,21 +557,33 @@ k_dav(i64 nl, i64 ld, int m, const double* __restrict__ V, const double* __restr
                 extra = fma(r, r, extra);
                 t[i] = ti;
             }
-        } else if (MODE == 1 || MODE == 2) {
-            double pr = 0.0;
-#pragma unroll 8
-            for (int j = 0; j < m; j++) pr = fma(s_c[j], __ldg(V + j * ld + ii), pr);
-            if (live) {
-                ti = t[i] - pr;
-                if (MODE == 1) { extra = fma(ti, ti, extra); t[i] = ti; }
-                else out[i] = ti * s_scale;
+#pragma unroll 16
+            for (int j = 0; j < m; j++) tile_s[j * 33 + lane] = __ldg(V + j * ld + ii) * ti;
+        } else {
+            // the other modes keep the tile's V entries in registers: one read, all loads in flight
+            double v[MCAP];
+#pragma unroll
+            for (int j = 0; j < MCAP; j++) v[j] = j < m ? __ldg(V + j * ld + ii) : 0.0;
+            if (MODE == 1 || MODE == 2) {
+                double pr = 0.0;
+#pragma unroll
+                for (int j = 0; j < MCAP; j++)
+                    if (j < m) pr = fma(s_c[j], v[j], pr);
+                if (live) {
+                    ti = t[i] - pr;
+                    if (MODE == 1) { extra = fma(ti, ti, extra); t[i] = ti; }
+                    else out[i] = ti * s_scale;
+                }
+            } else if (live) {
+                ti = w[i];
             }
-        } else if (live) {
-            ti = w[i];
+            if (MODE != 2) {
+#pragma unroll
+                for (int j = 0; j < MCAP; j++)
+                    if (j < m) tile_s[j * 33 + lane] = v[j] * ti;
+            }
         }
         if (MODE != 2) {
-#pragma unroll 8
-            for (int j = 0; j < m; j++) tile_s[j * 33 + lane] = __ldg(V + j * ld + ii) * ti;
             __syncwarp();
             if (lane < m) {
                 double a = 0.0;
