@@ -414,9 +414,10 @@ def _run_ours(args, out):
     warm = dets[:4096].contiguous()
     Pw = H.projected_csr(warm, fgk.H_SYM, packed=True, sort_rows=True).to_sell()
     Pw.matvec(torch.ones(warm.shape[0], dtype=torch.float64, device=dev))
-    if not args.no_krylov:      # cuSOLVER / cuBLAS handles and workspaces of the Krylov drivers
-        from flow_guided_krylov_b200.solvers import lowest_eigenpairs as _lep
+    if not args.no_krylov:      # cuSOLVER / cuBLAS handles and workspaces of the Krylov drivers (both forms)
+        from flow_guided_krylov_b200.solvers import lowest_eigenpairs as _lep, _LocalOp as _LO
         _lep(Pw, k=1, tol=1e-6, dense_max=0)
+        _lep(Pw, k=1, tol=1e-6, dense_max=0, sharded=_LO(Pw))
     del Pw, warm
     barrier()
     lo, hi = fdist.row_block(n, rank, world)
