@@ -825,6 +825,47 @@ def _run_ours(args, out):
             sk._subspace_op.close()
         del sk, nf_cfg
 
+    # ---- BASELINE configs[0..2]: real LiH / BeH2 / N2 STO-3G integrals (built-in PySCF-free front-end)
+    # through the drop-in classes: three selected-CI rounds from the HF determinant, then Stage 4 ----
+    small = None
+    if world == 1 and not args.no_small_configs:
+        from flow_guided_krylov_b200 import sto3g as _sto
+        small = {}
+        for name_, geo_, (no_, na_, nb_), k_ in (("lih", _sto.lih_geometry, (6, 2, 2), 150),
+                                                 ("beh2", _sto.beh2_geometry, (7, 3, 3), 200),
+                                                 ("n2", _sto.n2_geometry, (10, 7, 7), 300)):
+            I_ = _sto.compute_molecular_integrals(geo_())
+            Hm = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(I_.h1e, I_.h2e, I_.nuclear_repulsion, na_ + nb_, no_,
+                                                                 na_, nb_), dev)
+            for rep in range(2):                      # rep 0 warms the kernels up
+                ex_ = fgk.SelectedCIExpander(Hm, fgk.ResidualExpansionConfig(max_configs_per_iter=k_))
+                b_ = Hm.get_hf_state().unsqueeze(0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                es_ = []
+                for _ in range(3):
+                    b_, st_ = ex_.expand_basis(b_)
+                    es_.append(st_["final_energy"])
+                torch.cuda.synchronize()
+                t_sci = time.perf_counter() - t0
+            for rep in range(2):
+                torch.manual_seed(0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                sk_ = fgk.FlowGuidedSKQD(Hm, b_, fgk.SKQDConfig(max_krylov_dim=3, shots_per_krylov=2000))
+                Ps_ = sk_._build_subspace_hamiltonian()
+                torch.cuda.synchronize()
+                t_sub = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                rs_ = sk_.run_with_nf(progress=False)
+                torch.cuda.synchronize()
+                t_run = time.perf_counter() - t0
+            small[name_] = {"selected_ci_3_rounds_ms": 1e3 * t_sci, "basis_size": int(b_.shape[0]), "energies": es_,
+                            "fci_dim": int(sk_._subspace_dets.shape[0]), "subspace_H_nnz": Ps_.nnz,
+                            "subspace_setup_and_H_build_ms": 1e3 * t_sub, "run_with_nf_kdim3_ms": 1e3 * t_run,
+                            "best_stable_energy": rs_["best_stable_energy"]}
+            del Hm, sk_, Ps_
+
     # ---- PT2 selection at BASELINE configs[4] shape (48 orbitals, 12+12 electrons, 108,900-determinant
     # CAS basis, 270,648 connections per source): the sharded dedup / top-k path at size ----
     pt2_c4 = None
@@ -946,7 +987,7 @@ def _run_ours(args, out):
                            "one launch (k_peer_step): SELL H.v storing y into every rank's next vector over NVLink peer "
                            "memory, last CTA runs the flag barrier" if fused else "SELL H.v + NCCL all-gather"),
         "build": build, "build_packed": build_packed, "pt2": pt2, "pt2_config4": pt2_c4, "connections": conn, "krylov": krylov,
-        "packed_f32_storage": packed, "skqd_adaptive": skqd, "parity": parity,
+        "packed_f32_storage": packed, "skqd_adaptive": skqd, "configs_0_1_2": small, "parity": parity,
     }
     out.emit(json.dumps(line))
     if world > 1:
@@ -983,6 +1024,8 @@ def main():
                     help="PT2: radix partition (queues by top hash bits) in front of the hash map")
     ap.add_argument("--pt2-c4-sources", type=int, default=16384,
                     help="sources of the PT2 selection at configs[4] shape (48 orbitals); 0 disables the leg")
+    ap.add_argument("--no-small-configs", action="store_true",
+                    help="skip the LiH / BeH2 / N2 STO-3G leg (BASELINE configs[0..2]; N = 1 only)")
     ap.add_argument("--skqd-nf", type=int, default=2000, help="NF-basis size of the adaptive SKQD leg; 0 disables it")
     ap.add_argument("--skqd-max-set", type=int, default=200000, help="cap of the evolving determinant set of that leg")
     ap.add_argument("--conn-dets", type=int, default=1024, help="determinants of the connection-enumeration leg")

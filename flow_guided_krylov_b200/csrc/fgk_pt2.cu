@@ -676,6 +676,10 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
     i64 n_split = (4 * resident_warps + n_src - 1) / n_src;     // >= 4 waves of work units
     if (n_split < 1) n_split = 1;
     if (n_split > 256) n_split = 256;
+    {   // FGK_PT2_SPLIT: experiment knob (warps per source; more = fewer sources in flight at a time)
+        static const char* e_split = getenv("FGK_PT2_SPLIT");
+        if (e_split && atoi(e_split) > 0) n_split = atoi(e_split);
+    }
     i64 need = (n_src * n_split + FGK_WARPS_PER_BLOCK - 1) / FGK_WARPS_PER_BLOCK;
     i64 cap = (i64)fgk_sm_count(h->device) * 8;
     int grid = (int)(need < cap ? need : cap);
