@@ -8,6 +8,8 @@
 // lane; x is gathered through the read-only path and is L2-resident (8-16 MB at
 // 1e6 rows against 126 MB of L2).  Replaces scipy's csr_matvec under eigsh
 // (skqd.py:784, residual_expansion.py:435) and expm_multiply (skqd.py:291-293).
+#include <stdlib.h>
+
 #include "fgk_internal.cuh"
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double* p)
@@ -251,6 +253,14 @@ static int launch_spmv_sell(int64_t n_rows, const int64_t* slice_ptr, const int3
         return fgk_fail(FGK_ERR_ARG, "fgk_spmv_sell: vals must be 16-byte and cols 8-byte aligned");
     FGK_CUDA(cudaSetDevice(device));
     i64 n_slices = (n_rows + 31) / 32;
+    static const int unroll = getenv("FGK_SPMV_UNROLL") ? atoi(getenv("FGK_SPMV_UNROLL")) : 4;    // experiment knob
+    if (unroll == 8)
+        k_spmv_sell<CPLX, 8><<<(unsigned)n_slices, SELL_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            n_rows, (const i64*)slice_ptr, cols, vals, x, y);
+    else if (unroll == 2)
+        k_spmv_sell<CPLX, 2><<<(unsigned)n_slices, SELL_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            n_rows, (const i64*)slice_ptr, cols, vals, x, y);
+    else
     k_spmv_sell<CPLX, 4><<<(unsigned)n_slices, SELL_WARPS * 32, 0, (cudaStream_t)stream>>>(
         n_rows, (const i64*)slice_ptr, cols, vals, x, y);
     FGK_LAUNCH_CHECK();

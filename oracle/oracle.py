@@ -310,6 +310,12 @@ class OracleHam:
         n = len(H)
         if regularization > 0:
             H = H + regularization * np.eye(n)                         # :738-739
+        if np.linalg.cond(H) > 1e12:                                   # :742-750 -> _svd_ground_state, :809-843
+            U, s, Vh = np.linalg.svd(H, hermitian=True)
+            thr = 1e-10 * s.max()
+            H_reg = U @ np.diag(np.where(s > thr, s, thr)) @ Vh
+            w, v = np.linalg.eigh(H_reg)
+            return float(w[0]), (v[:, 0] if return_eigenvector else None)
         w, v = np.linalg.eigh(H)
         if n < 100 or return_eigenvector or not reference_compat:      # :754-758, :790-793
             return float(w[0]), v[:, 0]

@@ -708,6 +708,33 @@ def test_skqd_ground_state_energy_modes(fgk):
     assert abs(e0 - O.ground_state_energy(g["gse_big_basis"], True)[0]) < TOL
 
 
+def test_skqd_ill_conditioned_svd_fallback(fgk):
+    """skqd.py:742-750 + _svd_ground_state (:809-843): cond(H) > 1e12 sends the solve through the
+    SVD-regularised matrix.  Forced here by shifting E_nuc so that one eigenvalue of the projected H
+    vanishes (regularization = 0); engine vs the oracle's restatement of the same branch."""
+    from oracle import oracle as orc
+    g = load_golden("skqd_lih")
+    n_orb, na, nb = (int(x) for x in g["shape"])
+    basis = g["gse_small_basis"]
+    O0 = orc.OracleHam(g["h1"], g["g"], na, nb, 0.0)
+    D = O0.dense_H(basis)
+    lam = np.linalg.eigvalsh(0.5 * (D + D.T))
+    e_nuc = -float(lam[len(lam) // 2])                       # a middle eigenvalue becomes ~1e-16
+    integ = fgk.MolecularIntegrals(g["h1"].astype(np.float64), g["g"].astype(np.float64), e_nuc, na + nb, n_orb, na, nb)
+    H = fgk.MolecularHamiltonian(integ, device="cuda:0")
+    O = orc.OracleHam(g["h1"], g["g"], na, nb, e_nuc)
+    Ds = O.dense_H(basis)
+    assert np.linalg.cond(0.5 * (Ds + Ds.T)) > 1e12
+    sk = fgk.FlowGuidedSKQD(H, t64(g["nf_basis"]), fgk.SKQDConfig(max_krylov_dim=2))
+    e_vec, v = sk.compute_ground_state_energy(t64(basis), True, 0.0)
+    e_no, none = sk.compute_ground_state_energy(t64(basis), False, 0.0)
+    oe, ov = O.ground_state_energy(basis, True, regularization=0.0)
+    assert none is None and abs(e_vec - oe) < TOL and abs(e_no - oe) < TOL
+    assert abs(abs(np.dot(v.numpy(), ov)) - 1.0) < 1e-8
+    # the regularised solve differs from the plain one only in the clamped near-null mode
+    assert abs(e_vec - (lam[0] + e_nuc)) < 1e-8
+
+
 def test_skqd_run_with_nf_on_reference_samples(fgk):
     g = load_golden("skqd_lih")
     H, O, _ = make_pair(fgk, g)

@@ -223,3 +223,27 @@ def test_spmv_oracle_vs_numpy():
     z = x + 1j * rng.standard_normal(n)
     assert np.allclose(orc.csr_matvec(g["H_indptr"], g["H_indices"], g["H_data"], z), M @ z,
                        rtol=0, atol=1e-12)
+
+
+def test_ground_state_energy_svd_fallback_branch():
+    """oracle restatement of skqd.py:742-750 / :809-843: an ill-conditioned projected H (one
+    eigenvalue shifted to ~0, regularization 0) goes through the SVD-regularised matrix; the ground
+    energy is unchanged, the near-null mode is clamped to 1e-10 * s_max"""
+    g = load_golden("skqd_lih")
+    n_orb, na, nb = (int(x) for x in g["shape"])
+    basis = g["gse_small_basis"]
+    D = orc.OracleHam(g["h1"], g["g"], na, nb, 0.0).dense_H(basis)
+    lam = np.linalg.eigvalsh(0.5 * (D + D.T))
+    e_nuc = -float(lam[len(lam) // 2])
+    H = orc.OracleHam(g["h1"], g["g"], na, nb, e_nuc)
+    Ds = H.dense_H(basis)
+    S = 0.5 * (Ds + Ds.T)
+    assert np.linalg.cond(S) > 1e12
+    e, v = H.ground_state_energy(basis, True, regularization=0.0)
+    assert abs(e - (lam[0] + e_nuc)) < 1e-9
+    assert abs(v @ S @ v - e) < 1e-9
+    e2, none = H.ground_state_energy(basis, False, regularization=0.0)
+    assert none is None and abs(e2 - e) < 1e-12
+    # with the default regularisation the matrix is well conditioned again: plain branch
+    e3, _ = H.ground_state_energy(basis, True)
+    assert abs(e3 - (e + 1e-8)) < 1e-9
