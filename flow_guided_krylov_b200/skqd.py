@@ -170,7 +170,7 @@ class SampleBasedKrylovDiagonalization:
         from .expansion import pt2_select
         H, cfg = self.hamiltonian, self.config
         cap = int(_cfg(cfg, "max_subspace_size"))
-        amp = psi.abs()
+        amp = _solvers.complex_abs2(psi).sqrt()
         for _ in range(int(_cfg(cfg, "expand_rounds"))):
             m = self._subspace_dets.shape[0]
             budget = min(cap - m, int(_cfg(cfg, "expand_new_per_round")))
@@ -266,7 +266,7 @@ class SampleBasedKrylovDiagonalization:
 
     # :538-571 (sampling over the subspace amplitudes)
     def _sample_from_state(self, psi: torch.Tensor, num_samples: int):
-        probs = psi.abs() ** 2
+        probs = _solvers.complex_abs2(psi)
         # inverse-CDF sampling (torch.multinomial refuses more than 2^24 categories, and the
         # subspace may hold up to MAX_SUBSPACE determinants)
         cdf = torch.cumsum(probs, 0)
