@@ -267,12 +267,28 @@ k_peer_gather(const double* __restrict__ src, i64 n_words, const __grid_constant
 // partials in rank order -- identical bits on every rank, one launch, no library round trip
 // (an 8-rank NCCL all-reduce of a few doubles costs ~40 us, this ~6 us).
 __global__ void __launch_bounds__(256)
-k_peer_allreduce(const double* __restrict__ src, int n, double* __restrict__ dst, const __grid_constant__ PeerPtrs P,
-                 const __grid_constant__ PeerSync S, i64 area_offset, i64 slot_stride)
+k_peer_allreduce(const double* __restrict__ src, int n, int src_rows, double* __restrict__ dst,
+                 const __grid_constant__ PeerPtrs P, const __grid_constant__ PeerSync S, i64 area_offset, i64 slot_stride)
 {
-    for (int p = 0; p < S.world; p++) {
-        double* out = P.out[p] + area_offset + (i64)S.rank * slot_stride;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = src[i];
+    // src holds src_rows partial rows of n (one per CTA of the producing kernel): added first, in a
+    // fixed order (8 interleaved row groups per column, then the groups in order)
+    __shared__ double s_grp[8][128];
+    for (int i0 = 0; i0 < n; i0 += 128) {
+        const int ncol = n - i0 < 128 ? n - i0 : 128;
+        for (int idx = threadIdx.x; idx < ncol * 8; idx += blockDim.x) {
+            const int i = idx % ncol, gq = idx / ncol;
+            double v = 0.0;
+            for (int b = gq; b < src_rows; b += 8) v += src[(i64)b * n + i0 + i];
+            s_grp[gq][i] = v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncol; i += blockDim.x) {
+            double v = 0.0;
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) v += s_grp[gq][i];
+            for (int p = 0; p < S.world; p++) P.out[p][area_offset + (i64)S.rank * slot_stride + i0 + i] = v;
+        }
+        __syncthreads();
     }
     peer_finish(S);             // gridDim = 1: this CTA is the last one; arrives and waits for every peer
     __syncthreads();
@@ -349,12 +365,13 @@ extern "C" int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* con
     return FGK_OK;
 }
 
-extern "C" int fgk_peer_allreduce_sum(const double* src, int64_t n, double* dst, double* const* peer_scratch_host,
+extern "C" int fgk_peer_allreduce_sum(const double* src, int64_t n, int64_t src_rows, double* dst, double* const* peer_scratch_host,
                                       int64_t slot_stride, int area, uint64_t* const* peer_flags_host, int rank,
                                       int world, uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag,
                                       int device, void* stream)
 {
-    if (!src || !dst || !peer_scratch_host || n < 0 || n > slot_stride || slot_stride < 1 || (area != 0 && area != 1))
+    if (!src || !dst || !peer_scratch_host || n < 0 || n > slot_stride || slot_stride < 1 || (area != 0 && area != 1) ||
+        src_rows < 1 || src_rows > (1 << 20))
         return fgk_fail(FGK_ERR_ARG, "fgk_peer_allreduce_sum: bad argument");
     PeerSync S;
     int rc = fill_sync(S, peer_flags_host, rank, world, epoch, done_counter, err_flag);
@@ -362,8 +379,8 @@ extern "C" int fgk_peer_allreduce_sum(const double* src, int64_t n, double* dst,
     FGK_CUDA(cudaSetDevice(device));
     PeerPtrs P;
     for (int p = 0; p < PEER_MAX; p++) P.out[p] = p < world ? peer_scratch_host[p] : nullptr;
-    k_peer_allreduce<<<1, 256, 0, (cudaStream_t)stream>>>(src, (int)n, dst, P, S, (i64)area * world * slot_stride,
-                                                          slot_stride);
+    k_peer_allreduce<<<1, 256, 0, (cudaStream_t)stream>>>(src, (int)n, (int)src_rows, dst, P, S,
+                                                          (i64)area * world * slot_stride, slot_stride);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }

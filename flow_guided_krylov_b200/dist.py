@@ -428,9 +428,25 @@ class FusedShardedOperator:
         area = self._ar_calls & 1
         self._ar_calls += 1
         nat.check(nat.lib().fgk_peer_allreduce_sum(
-            C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(t.data_ptr()), self._scratch, self.AR_SLOT, area,
+            C.c_void_p(t.data_ptr()), t.numel(), 1, C.c_void_p(t.data_ptr()), self._scratch, self.AR_SLOT, area,
             *self._sync_args()))
         return t
+
+    def reduce_partials(self, partial, rows, n):
+        """sum of `rows` partial rows of n doubles (fgk_davidson_step's per-CTA rows, contiguous at the
+        start of `partial`) over the rows and over the ranks, in ONE launch -> new (n,) tensor"""
+        import ctypes as C
+        from . import _native as nat
+        out = torch.empty(n, dtype=torch.float64, device=partial.device)
+        if self.world == 1 or n > self.AR_SLOT:
+            out.copy_(partial.view(-1)[: rows * n].view(rows, n).sum(dim=0))
+            return self.allreduce_sum_(out)
+        area = self._ar_calls & 1
+        self._ar_calls += 1
+        nat.check(nat.lib().fgk_peer_allreduce_sum(
+            C.c_void_p(partial.data_ptr()), n, rows, C.c_void_p(out.data_ptr()), self._scratch, self.AR_SLOT, area,
+            *self._sync_args()))
+        return out
 
     def check(self):
         e = int(self._err.item())

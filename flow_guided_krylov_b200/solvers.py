@@ -246,8 +246,12 @@ def _davidson_fused(op, k, tol, max_iter, max_space, v0, phases):
             mode, nl, nl, mm, nat.ptr(V), nat.ptr(W), host_coef, nat.ptr(dev_coef), nat.ptr(tt), float(theta),
             nat.ptr(diag), nat.ptr(tvec), nat.ptr(w), nat.ptr(out), nat.ptr(partial), G_, nat.ptr(nrm), dev_i, st))
 
+    fused_reduce = getattr(op, "reduce_partials", None)
+
     def reduced(mm):
         """block partials -> one vector (rows added in order) -> sum over the ranks"""
+        if fused_reduce is not None:
+            return fused_reduce(partial, G_, mm + 1)
         return allsum(partial.view(-1)[: G_ * (mm + 1)].view(G_, mm + 1).sum(dim=0))
 
     w_out = X = None

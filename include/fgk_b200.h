@@ -267,10 +267,11 @@ int fgk_davidson_step(int mode, int64_t n_local, int64_t ld, int m, const double
                       int n_blocks, double* nrm_out, int device, void* stream);
 
 /* Small all-reduce (sum) of n <= slot_stride doubles over peer memory: the dot products of a
- * row-sharded Krylov iteration.  peer_scratch[p]: rank p's scratch, 2 * world * slot_stride doubles;
- * area alternates 0 / 1 between consecutive calls.  Partials are added in rank order: identical
- * bits on every rank.  src and dst may alias. */
-int fgk_peer_allreduce_sum(const double* src, int64_t n, double* dst, double* const* peer_scratch,
+ * row-sharded Krylov iteration.  src holds src_rows rows of n doubles (the per-CTA partial rows of
+ * fgk_davidson_step; 1 for a plain vector), added in row order first.  peer_scratch[p]: rank p's
+ * scratch, 2 * world * slot_stride doubles; area alternates 0 / 1 between consecutive calls.
+ * Partials are added in rank order: identical bits on every rank.  dst (n doubles) may alias row 0. */
+int fgk_peer_allreduce_sum(const double* src, int64_t n, int64_t src_rows, double* dst, double* const* peer_scratch,
                            int64_t slot_stride, int area, uint64_t* const* peer_flags, int rank, int world,
                            uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
 
