@@ -87,12 +87,24 @@ extern "C" int fgk_ham_create(const double* h1_host, const double* g_host, int n
     for (int p = 0; p < n_orb; p++) dt[p] = T.hdiag[p];
     for (size_t i = 0; i < nn; i++) { dt[npad + i] = T.nib_jk[i]; dt[npad + nn + i] = T.nib_jab[i]; }
     for (size_t i = 0; i < n2; i++) { jk[i] = T.jks[i]; jk[n2 + i] = T.jab[i]; }
+    // integral tables h1 | g | w in one buffer, every segment padded to 16 bytes: a single TMA bulk
+    // copy stages them in shared memory when they fit (n_orb <= 12: 166 KB; all of the reference's
+    // molecules), see k_conn
+    auto pad4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
+    const size_t o_g = pad4(T.h1.size()), o_w = o_g + pad4(T.g.size()), n_it = o_w + pad4(T.w.size());
+    std::vector<float> it(n_it, 0.f);
+    std::copy(T.h1.begin(), T.h1.end(), it.begin());
+    std::copy(T.g.begin(), T.g.end(), it.begin() + o_g);
+    std::copy(T.w.begin(), T.w.end(), it.begin() + o_w);
     int rc;
-    if ((rc = upload(T.h1, &H->h1)) || (rc = upload(T.g, &H->g)) || (rc = upload(T.w, &H->w)) ||
-        (rc = upload(dt, &H->dtab)) || (rc = upload(jk, &H->jkab))) {
+    if ((rc = upload(it, &H->itab)) || (rc = upload(dt, &H->dtab)) || (rc = upload(jk, &H->jkab))) {
         delete H;
         return rc;
     }
+    H->h1 = H->itab;
+    H->g = H->itab + o_g;
+    H->w = H->itab + o_w;
+    H->itab_bytes = n_it * sizeof(float) <= 176 * 1024 ? (unsigned)(n_it * sizeof(float)) : 0u;
     const size_t bytes = dt.size() * sizeof(double);
     const bool nib_ok = bytes <= 208 * 1024;
     H->dtab_bytes = nib_ok ? (unsigned)bytes : 0;
@@ -110,7 +122,7 @@ extern "C" int fgk_ham_destroy(fgk_ham_t h)
 {
     if (!h) return FGK_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->h1); cudaFree(h->g); cudaFree(h->w);
+    cudaFree(h->itab);
     cudaFree(h->dtab); cudaFree(h->jkab);
     delete h;
     return FGK_OK;
@@ -250,18 +262,35 @@ extern "C" int fgk_diag(fgk_ham_t h, const uint64_t* dets, int64_t n, double* ou
 // one warp per source determinant.  FILL = false: count survivors of the
 // reference's |val| > 1e-12 filters; FILL = true: write them at offsets[j] + rank,
 // rank = position in the reference's emission order, obtained by ballot + popc.
-template <bool FILL>
+// STAGED: the integral tables h1 | g | w (one contiguous buffer) are staged in shared memory by a
+// single TMA bulk copy (cp.async.bulk + mbarrier, as k_diag does for the diagonal tables) and
+// read with ld.shared; used when they fit (n_orb <= 12).  Larger tables (4.2 MB each at 32
+// orbitals) stay L2-resident and are read through the read-only path.
+template <bool STAGED> struct ConnLoader { typedef LdgF type; };
+template <> struct ConnLoader<true> { typedef LdsF type; };
+
+template <bool FILL, bool STAGED>
 __global__ void __launch_bounds__(FGK_BLOCK)
-k_conn(HamView H, const fgk_det* __restrict__ dets, i64 n, i64* __restrict__ counts,
+k_conn(HamView H, unsigned tab_bytes, const fgk_det* __restrict__ dets, i64 n, i64* __restrict__ counts,
        const i64* __restrict__ offsets, fgk_det* __restrict__ out_dets,
        float* __restrict__ out_elems, i64* __restrict__ out_src)
 {
+    extern __shared__ __align__(128) unsigned char s_itab[];
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
+    if (STAGED) {
+        tma_stage_table(s_itab, H.h1, tab_bytes, &s_mbar);
+        const float* s_tab = reinterpret_cast<const float*>(s_itab);
+        const float* g0 = H.h1;
+        H.g = s_tab + (H.g - g0);
+        H.w = s_tab + (H.w - g0);
+        H.h1 = s_tab;
+    }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
     const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
-    LdgF ldf;
+    typename ConnLoader<STAGED>::type ldf;
     for (i64 j = warp0; j < n; j += nwarps) {
         ulonglong2 dv = __ldg(reinterpret_cast<const ulonglong2*>(dets) + j);
         fgk_det d = {dv.x, dv.y};
@@ -305,6 +334,23 @@ k_conn(HamView H, const fgk_det* __restrict__ dets, i64 n, i64* __restrict__ cou
     }
 }
 
+static int conn_ctas_per_sm(unsigned tab_bytes)
+{
+    int c = (int)((200u * 1024u) / (tab_bytes + 4096u));
+    return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
+
+template <bool FILL>
+static int conn_smem_attr(unsigned bytes)
+{
+    static bool done = false;           // per instantiation; the limit is per function, not per device state
+    if (!done && bytes > 48 * 1024) {
+        FGK_CUDA(cudaFuncSetAttribute(k_conn<FILL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        done = true;
+    }
+    return FGK_OK;
+}
+
 extern "C" int fgk_conn_count(fgk_ham_t h, const uint64_t* dets, int64_t n, int64_t* counts,
                               void* stream)
 {
@@ -312,8 +358,16 @@ extern "C" int fgk_conn_count(fgk_ham_t h, const uint64_t* dets, int64_t n, int6
     if (n == 0) return FGK_OK;
     if (!dets || !counts || n < 0) return fgk_fail(FGK_ERR_ARG, "fgk_conn_count: bad argument");
     FGK_CUDA(cudaSetDevice(h->device));
-    k_conn<false><<<grid_for(n, FGK_WARPS_PER_BLOCK, h->device, 8), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, (const fgk_det*)dets, n, (i64*)counts, nullptr, nullptr, nullptr, nullptr);
+    if (h->itab_bytes) {
+        int rc = conn_smem_attr<false>(h->itab_bytes);
+        if (rc != FGK_OK) return rc;
+        // the staging copy is paid per CTA: long-lived CTAs (grid-stride over the determinants), as many
+        // per SM as the staged tables leave room for
+        k_conn<false, true><<<grid_for(n, 4 * FGK_WARPS_PER_BLOCK, h->device, conn_ctas_per_sm(h->itab_bytes)), FGK_BLOCK, h->itab_bytes, (cudaStream_t)stream>>>(
+            h->v, h->itab_bytes, (const fgk_det*)dets, n, (i64*)counts, nullptr, nullptr, nullptr, nullptr);
+    } else
+    k_conn<false, false><<<grid_for(n, FGK_WARPS_PER_BLOCK, h->device, 8), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+        h->v, 0u, (const fgk_det*)dets, n, (i64*)counts, nullptr, nullptr, nullptr, nullptr);
     FGK_LAUNCH_CHECK();
     return FGK_OK;
 }
@@ -325,8 +379,15 @@ extern "C" int fgk_conn_fill(fgk_ham_t h, const uint64_t* dets, int64_t n, const
     if (n == 0) return FGK_OK;
     if (!dets || !offsets || n < 0) return fgk_fail(FGK_ERR_ARG, "fgk_conn_fill: bad argument");
     FGK_CUDA(cudaSetDevice(h->device));
-    k_conn<true><<<grid_for(n, FGK_WARPS_PER_BLOCK, h->device, 8), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
-        h->v, (const fgk_det*)dets, n, nullptr, (const i64*)offsets, (fgk_det*)out_dets, out_elems,
+    if (h->itab_bytes) {
+        int rc = conn_smem_attr<true>(h->itab_bytes);
+        if (rc != FGK_OK) return rc;
+        k_conn<true, true><<<grid_for(n, 4 * FGK_WARPS_PER_BLOCK, h->device, conn_ctas_per_sm(h->itab_bytes)), FGK_BLOCK, h->itab_bytes, (cudaStream_t)stream>>>(
+            h->v, h->itab_bytes, (const fgk_det*)dets, n, nullptr, (const i64*)offsets, (fgk_det*)out_dets, out_elems,
+            (i64*)out_src);
+    } else
+    k_conn<true, false><<<grid_for(n, FGK_WARPS_PER_BLOCK, h->device, 8), FGK_BLOCK, 0, (cudaStream_t)stream>>>(
+        h->v, 0u, (const fgk_det*)dets, n, nullptr, (const i64*)offsets, (fgk_det*)out_dets, out_elems,
         (i64*)out_src);
     FGK_LAUNCH_CHECK();
     return FGK_OK;

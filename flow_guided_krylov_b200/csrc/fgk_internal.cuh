@@ -35,7 +35,10 @@ int fgk_fail(int code, const char* fmt, ...);
 struct fgk_ham {
     int device;
     HamView v;          // device pointers
-    float *h1, *g, *w;
+    float *h1, *g, *w;  // views into itab
+    float* itab;        // [h1 | g | w] float32 in ONE contiguous buffer (16-byte granular segments)
+    unsigned itab_bytes;  // its size when it fits shared memory next to the kernels' own (else 0):
+                          // one TMA bulk copy stages all integral tables for the connection enumerator
     double* dtab;       // [h_pp (padded to even)] [nibble (J-K) rows] [nibble J rows]: one TMA bulk copy
     unsigned dtab_bytes;  // 0 when the nibble tables would not fit shared memory (n_orb > 56)
     double* jkab;       // plain jks | jab (n*n each), for the pair-loop fallback
@@ -146,6 +149,15 @@ struct LdgD { __device__ __forceinline__ double operator()(const double* p) cons
 
 // explicit shared-space load for tables staged in shared memory (a table pointer rebased onto
 // the staging buffer is a generic address to the compiler: it emits LD instead of LDS)
+struct LdsF {
+    __device__ __forceinline__ float operator()(const float* p) const
+    {
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        return v;
+    }
+};
+
 struct LdsD {
     __device__ __forceinline__ double operator()(const double* p) const
     {
