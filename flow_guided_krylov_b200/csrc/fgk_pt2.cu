@@ -203,14 +203,30 @@ k_pt2_accumulate(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_
 // 128-bit hash) for every connection, owned or not.  As in k_projh3 the alpha-beta table offset
 // and sign parity split into per-single parts, precomputed once per work unit in shared memory:
 // entry = hole | particle << 8 | pk << 16 | s1 << 17 | owned << 18.
-template <int BPS>
+// STAGED (n_orb <= 12, every molecule of the reference): the integral tables h1 | g | w are staged in
+// shared memory by one TMA bulk copy per CTA, behind the singles-list area, and read with ld.shared.
+template <bool STAGED> struct Pt2Loader { typedef LdgF type; };
+template <> struct Pt2Loader<true> { typedef LdsF type; };
+
+template <int BPS, bool STAGED>
 __global__ void __launch_bounds__(FGK_BLOCK, BPS)
 k_pt2_accumulate2(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src_idx,
                   const double* __restrict__ coeff, i64 n_src, int n_split, int mode, unsigned n_a,
-                  unsigned a_id, unsigned n_d, unsigned d_id, int cap)
+                  unsigned a_id, unsigned n_d, unsigned d_id, int cap, unsigned tab_bytes, unsigned tab_offset)
 {
-    extern __shared__ __align__(16) unsigned s_ent[];           // [warps][2][cap]
+    extern __shared__ __align__(128) unsigned char s_dyn2[];    // [tables (tab_offset bytes in)] after [warps][2][cap] entries
+    unsigned* const s_ent = reinterpret_cast<unsigned*>(s_dyn2);
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ WarpLists s_lists[FGK_WARPS_PER_BLOCK];
+    if (STAGED) {
+        unsigned char* dst = s_dyn2 + tab_offset;
+        tma_stage_table(dst, H.h1, tab_bytes, &s_mbar);
+        const float* s_tab = reinterpret_cast<const float*>(dst);
+        const float* g0 = H.h1;
+        H.g = s_tab + (H.g - g0);
+        H.w = s_tab + (H.w - g0);
+        H.h1 = s_tab;
+    }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const i64 warp0 = (i64)blockIdx.x * FGK_WARPS_PER_BLOCK + wib;
     const i64 nwarps = (i64)gridDim.x * FGK_WARPS_PER_BLOCK;
@@ -218,7 +234,7 @@ k_pt2_accumulate2(HamView H, IndexView I, Pt2View W, const i64* __restrict__ src
     const int n = H.n_orb, n2 = n * n;
     unsigned* const La = s_ent + (size_t)wib * 2 * cap;
     unsigned* const Lb = La + cap;
-    LdgF ldf;
+    typename Pt2Loader<STAGED>::type ldf;
     i64 tested = 0;
     auto mine = [&](u64 alpha_word) -> bool {
         return n_a <= 1 || (unsigned)((word_hash(alpha_word) >> 40) % n_a) == a_id;
@@ -720,8 +736,16 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
         static const bool per_candidate = getenv("FGK_PT2_PER_CANDIDATE_BUCKETS") != nullptr;
         if (!per_candidate) {
             // buckets by alpha string (see k_pt2_accumulate2)
-            if (smem > 40 * 1024)
-                FGK_CUDA(cudaFuncSetAttribute(k_pt2_accumulate2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned tab_off = (unsigned)((smem + 127) & ~(size_t)127);
+            const bool staged = h->itab_bytes && tab_off + h->itab_bytes <= 200u * 1024u;
+            if (staged) {
+                static bool attr = false;
+                if (!attr) {
+                    FGK_CUDA(cudaFuncSetAttribute(k_pt2_accumulate2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+                    attr = true;
+                }
+            } else if (smem > 40 * 1024)
+                FGK_CUDA(cudaFuncSetAttribute(k_pt2_accumulate2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             unsigned n_a = (unsigned)n_pass;                 // first level: largest divisor <= 64
             if (n_a > 64) {
                 n_a = 1;
@@ -729,9 +753,18 @@ extern "C" int fgk_pt2_accumulate(fgk_ham_t h, fgk_index_t idx, fgk_pt2_t ws, co
                     if ((unsigned)n_pass % dv == 0) { n_a = dv; break; }
             }
             const unsigned n_d = (unsigned)n_pass / n_a;
-            k_pt2_accumulate2<4><<<grid, FGK_BLOCK, smem, (cudaStream_t)stream>>>(
+            if (staged) {
+                int per_sm = (int)((200u * 1024u) / (tab_off + h->itab_bytes + 4096u));
+                per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+                const i64 cap2 = (i64)fgk_sm_count(h->device) * per_sm;
+                const int grid2 = (int)(need < cap2 ? need : cap2);
+                k_pt2_accumulate2<1, true><<<grid2, FGK_BLOCK, tab_off + h->itab_bytes, (cudaStream_t)stream>>>(
+                    h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, n_a,
+                    (unsigned)pass_id % n_a, n_d, (unsigned)pass_id / n_a, scap, h->itab_bytes, tab_off);
+            } else
+            k_pt2_accumulate2<4, false><<<grid, FGK_BLOCK, smem, (cudaStream_t)stream>>>(
                 h->v, idx->v, ws->v, (const i64*)src_idx, coeff, n_src, (int)n_split, mode, n_a,
-                (unsigned)pass_id % n_a, n_d, (unsigned)pass_id / n_a, scap);
+                (unsigned)pass_id % n_a, n_d, (unsigned)pass_id / n_a, scap, 0u, 0u);
         }
         else if (bps == 8) FGK_PT2_LAUNCH(8, false);
         else if (bps == 6) FGK_PT2_LAUNCH(6, false);
