@@ -11,8 +11,10 @@ SRC="${1:-/root/reference}"
 if [ ! -d "$SRC/src" ]; then
     echo "vendor_ref: $SRC/src not found (nothing vendored)"; exit 0
 fi
+[ -d "$ROOT/oracle/_ref/src" ] && chmod -R u+w "$ROOT/oracle/_ref/src"
 rm -rf "$ROOT/oracle/_ref/src"
 mkdir -p "$ROOT/oracle/_ref"
 cp -r "$SRC/src" "$ROOT/oracle/_ref/src"
+chmod -R u+w "$ROOT/oracle/_ref/src"
 find "$ROOT/oracle/_ref" -name __pycache__ -type d -prune -exec rm -rf {} +
 echo "vendor_ref: copied $SRC/src -> oracle/_ref/src ($(find "$ROOT/oracle/_ref/src" -name '*.py' | wc -l) files)"
