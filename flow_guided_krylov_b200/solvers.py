@@ -229,8 +229,21 @@ def _davidson_fused(op, k, tol, max_iter, max_space, v0, phases):
     m = nb
     V[:m] = V0.T
     del V0
-    for i in range(m):
-        op.matvec_local(V[i], out=W[i])
+
+    def apply_h(j0, j1):
+        """W[j] = H V[j] for j0 <= j < j1.  Two real vectors ride in ONE complex product (x1 + i x2):
+        the packed complex H.v costs 12 % more than the real one (2.93 vs 2.61 ms on configs[3]), so a
+        pair costs 0.56 of two separate products."""
+        j = j0
+        while j + 1 < j1:
+            y = op.matvec_local(torch.complex(V[j], V[j + 1]))
+            W[j].copy_(y.real)
+            W[j + 1].copy_(y.imag)
+            j += 2
+        if j < j1:
+            op.matvec_local(V[j], out=W[j])
+
+    apply_h(0, m)
     T = np.zeros((m_max, m_max))
     T[:m, :m] = allsum((V[:m] @ W[:m].T).contiguous()).cpu().numpy()
 
@@ -291,8 +304,7 @@ def _davidson_fused(op, k, tol, max_iter, max_space, v0, phases):
             norms.append(nrm)
             added += 1
         ph.mark("correction_orth")
-        for j in range(m, m + added):
-            op.matvec_local(V[j], out=W[j])
+        apply_h(m, m + added)
         ph.mark("matvec")
         cols = []
         for j in range(m, m + added):
