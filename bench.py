@@ -28,7 +28,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 from itertools import combinations
 from math import comb

@@ -189,8 +189,8 @@ def pt2_select_sharded(ham, index, coeffs, energy, k, mode=None, workspace=None,
     Returns (selected dets, scores, stats); identical on all ranks.  With one rank this is
     expansion.pt2_select."""
     from . import _native as nat
-    from .expansion import (Pt2Workspace, _raw_connections_per_det, default_pt2_workspace,
-                            planned_passes, pt2_select, select_top_k)
+    from .expansion import (_raw_connections_per_det, default_pt2_workspace, planned_passes, pt2_select,
+                            select_top_k)
     mode = nat.PT2_SUM if mode is None else mode
     rank, ws = world()
     if ws == 1:

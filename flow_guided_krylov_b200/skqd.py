@@ -31,7 +31,7 @@ The Trotter / Pauli / spin-lattice branches (:421-536) are out of scope.
 """
 from dataclasses import dataclass
 from math import comb
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
