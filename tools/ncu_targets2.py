@@ -14,7 +14,7 @@ H = fgk.MolecularHamiltonian(fgk.MolecularIntegrals(h1, g, 0.0, 16, 32, 8, 8), d
 dets = torch.from_numpy(cas_window_basis(32, 4, 14, 4).view(np.int64)).to(dev)
 n = dets.shape[0]
 P = H.projected_packed(dets, fgk.H_SYM, packed=True)
-w, v = solvers._davidson_fused(solvers._LocalOp(P), 1, 1e-9, 12, None, None, None)
+w, v = solvers._davidson_fused(solvers._LocalOp(P), 1, 1e-9, 3, None, None, None)
 psi = torch.zeros(n, dtype=torch.complex128, device=dev)
 psi[0] = 1.0
 mu = float(P.diagonal().sum()) / n
