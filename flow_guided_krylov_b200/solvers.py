@@ -538,8 +538,8 @@ def expm_multiply(P, psi, t, matvec=None, mu=None, norm1=None, allreduce_max=Non
     normal operators of this path the Taylor terms are governed by the spectral radius, which
     is several times smaller than the 1-norm (2,221 entries per row on configs[3]), so far fewer
     products are needed.  The choice is checked a posteriori: rounding errors of the series are
-    bounded by u * sum_j ||term_j||; if that sum exceeds 1e3 ||result|| the step is redone
-    with the 1-norm parameters.
+    bounded by u * sum_j ||term_j||; if that sum exceeds 1e3 ||result||, or the last of the m*
+    terms is still above 1e-9 ||result||, the step is redone with the 1-norm parameters.
 
     On CUDA vectors one fused kernel per term (fgk_taylor_update_z) forms B <- c (H B - mu B),
     F <- F + B and both infinity norms."""
@@ -575,6 +575,8 @@ def expm_multiply(P, psi, t, matvec=None, mu=None, norm1=None, allreduce_max=Non
             c1 = inf_norm(B)
             total = c1
             nf = c1
+            c2 = 0.0
+            converged = False
             for j in range(1, m_star + 1):
                 c = t / (s * j)
                 if fused:
@@ -590,10 +592,11 @@ def expm_multiply(P, psi, t, matvec=None, mu=None, norm1=None, allreduce_max=Non
                     nf = inf_norm(F)
                 total += c2
                 if c1 + c2 <= tol * nf:
+                    converged = True
                     break
                 c1 = c2
-            if guard and total > 1e3 * nf:
-                return None                              # cancellation: the estimate was too small
+            if guard and (total > 1e3 * nf or (not converged and c2 > 1e-9 * nf)):
+                return None        # cancellation, or the series is not done after m* terms: the estimate was too small
             F = F * eta
             B = F.clone()
         return F

@@ -121,6 +121,77 @@ def test_expm_multiply_matches_scipy():
     assert np.abs(big.numpy() - sp_expm(-2.5j * M, psi)).max() < 1e-11
 
 
+def test_expm_multiply_spectral_radius_scaling_and_guard():
+    """Taylor scaling by the estimated spectral radius: same result as the 1-norm scaling with
+    fewer products on the reference's (non-Hermitian, F3) subspace matrix; an estimate that is far
+    too small trips the a-posteriori check and falls back to the 1-norm parameters"""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import expm_multiply as sp_expm
+    from flow_guided_krylov_b200.solvers import (_taylor_parameters, complex_abs2, expm_multiply,
+                                                 spectral_radius_estimate)
+    g = load_golden("skqd_lih")
+    n = len(g["H_indptr"]) - 1
+    M = sp.csr_matrix((g["H_data"], g["H_indices"], g["H_indptr"]), shape=(n, n))
+    A = torch.from_numpy(M.toarray())
+    op = DenseOp(A)
+    calls = [0]
+
+    def mv(x):
+        calls[0] += 1
+        return A.to(x.dtype) @ x
+    psi = torch.zeros(n, dtype=torch.complex128)
+    psi[int(g["hf_index"])] = 1.0
+    mu = float(torch.diagonal(A).mean())
+    d = torch.diagonal(A)
+    norm1 = float((A.abs().sum(0) - d.abs() + (d - mu).abs()).max())
+    rho = spectral_radius_estimate(mv, n, mu, "cpu", iters=30)
+    lam = np.abs(np.linalg.eigvals(M.toarray() - mu * np.eye(n))).max()
+    assert 0.7 * lam <= rho <= 1.05 * lam and rho < norm1
+    for t in (-0.1j, -2.5j):
+        ref = sp_expm(t * M, psi.numpy())
+        calls[0] = 0
+        a = expm_multiply(op, psi, t, matvec=mv, mu=mu, norm1=norm1)
+        n_a = calls[0]
+        calls[0] = 0
+        b = expm_multiply(op, psi, t, matvec=mv, mu=mu, norm1=norm1, rho=rho)
+        n_b = calls[0]
+        assert np.abs(a.numpy() - ref).max() < 1e-11 and np.abs(b.numpy() - ref).max() < 1e-11
+        assert n_b <= n_a
+    # a far too small estimate (symmetrised matrix: a unitary, well-conditioned evolution): the series is
+    # not finished after m* terms, the a-posteriori check redoes the step with the 1-norm parameters
+    Ssym = 0.5 * (M + M.T)
+    As = torch.from_numpy(Ssym.toarray())
+
+    def mvs(x):
+        calls[0] += 1
+        return As.to(x.dtype) @ x
+    ds = torch.diagonal(As)
+    norm1s = float((As.abs().sum(0) - ds.abs() + (ds - mu).abs()).max())
+    ref_s = sp_expm(-3.0j * Ssym, psi.numpy())
+    calls[0] = 0
+    good = expm_multiply(DenseOp(As), psi, -3.0j, matvec=mvs, mu=mu, norm1=norm1s)
+    n_good = calls[0]
+    calls[0] = 0
+    c = expm_multiply(DenseOp(As), psi, -3.0j, matvec=mvs, mu=mu, norm1=norm1s, rho=0.02 * rho)
+    assert np.abs(c.numpy() - ref_s).max() < 1e-10 and np.abs(good.numpy() - ref_s).max() < 1e-10
+    assert calls[0] > n_good                                  # the aborted attempt + the redone step
+    assert abs(float(torch.linalg.norm(c)) - 1.0) < 1e-10
+    # parameter table: cost grows with the argument, degree capped in spectral-radius mode
+    costs = [m * s_ for m, s_ in (_taylor_parameters(a_) for a_ in (0.01, 0.1, 1.0, 10.0, 100.0))]
+    assert costs == sorted(costs) and _taylor_parameters(0.0) == (1, 1)
+    assert all(_taylor_parameters(a_, 30)[0] <= 30 for a_ in (0.5, 5.0, 50.0, 500.0))
+    z = torch.tensor([3 + 4j, 1j], dtype=torch.complex128)
+    assert torch.equal(complex_abs2(z), torch.tensor([25.0, 1.0], dtype=torch.float64))
+
+
+def test_pt2_pass_planning():
+    from flow_guided_krylov_b200.expansion import DISTINCT_PER_RAW, planned_passes
+    assert planned_passes(1000, 10 ** 9) == 1
+    assert planned_passes(4_434_296_832, 1_700_000_000) == 2            # configs[4] shape on one GPU
+    assert planned_passes(4_434_296_832, 440_000_000, 8) == 1           # ... on eight
+    assert planned_passes(10 ** 9, 10 ** 6) == int(np.ceil(DISTINCT_PER_RAW * 1e9 / 1e6))
+
+
 def test_select_top_k_ties_and_order():
     from flow_guided_krylov_b200.expansion import select_top_k
     dets = torch.tensor([[5, 1], [2, 9], [2, 3], [7, 0], [1, 1], [2, 4]], dtype=torch.int64)
