@@ -65,6 +65,8 @@ _SIGNATURES = {
     "fgk_peer_step": (ci, [i64, vp, vp, vp, vp, vp, C.POINTER(vp), ci, i64, C.POINTER(vp), ci, ci, C.c_uint64,
                            vp, vp, ci, vp]),
     "fgk_peer_allreduce_sum": (ci, [vp, i64, i64, vp, C.POINTER(vp), i64, ci, C.POINTER(vp), ci, ci, C.c_uint64, vp, vp, ci, vp]),
+    "fgk_peer_matvec_host": (ci, [i64, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, ci, i64, C.POINTER(vp),
+                                  ci, ci, C.c_uint64, vp, vp, ci, vp]),
     "fgk_peer_gather": (ci, [vp, i64, C.POINTER(vp), i64, C.POINTER(vp), ci, ci, C.c_uint64, vp, vp, ci, vp]),
     "fgk_pt2_create": (ci, [i64, i64, vp, vp, vp, ci, C.POINTER(vp)]),
     "fgk_pt2_destroy": (ci, [vp]),

@@ -365,6 +365,36 @@ extern "C" int fgk_peer_gather(const void* src_local, int64_t n_bytes, void* con
     return FGK_OK;
 }
 
+// Host-buffer product on N GPUs in ONE library call: this rank's slice of x comes from (pinned)
+// host memory, the slices are exchanged over peer memory, one fused step runs, and the rank's rows
+// of y go back to (pinned) host memory; returns when y_host is complete.  Five host-side calls
+// (copy, gather, step, copy, synchronise) folded into one entry point: the e2e step at N = 8 is
+// ~0.65 ms, of which the interpreter overhead of five separate calls was ~0.05 ms.
+extern "C" int fgk_peer_matvec_host(int64_t n_rows, const int64_t* slice_ptr, const void* cols_or_packed,
+                                    const double* vals, const double* diag, const void* x_host_slice,
+                                    void* x_dev_slice, double* const* peer_cur_host, double* const* peer_next_host,
+                                    void* y_host, int flags, int64_t row_offset, uint64_t* const* peer_flags_host,
+                                    int rank, int world, uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag,
+                                    int device, void* stream)
+{
+    if (!x_host_slice || !x_dev_slice || !peer_cur_host || !peer_next_host || !y_host || rank < 0 || rank >= world)
+        return fgk_fail(FGK_ERR_ARG, "fgk_peer_matvec_host: bad argument");
+    FGK_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t w = (flags & FGK_PEER_COMPLEX) ? 16 : 8;
+    FGK_CUDA(cudaMemcpyAsync(x_dev_slice, x_host_slice, (size_t)(w * n_rows), cudaMemcpyHostToDevice, st));
+    int rc = fgk_peer_gather(x_dev_slice, w * n_rows, (void* const*)peer_cur_host, w * row_offset, peer_flags_host, rank,
+                             world, epoch, done_counter, err_flag, device, stream);
+    if (rc != FGK_OK) return rc;
+    rc = fgk_peer_step(n_rows, slice_ptr, cols_or_packed, vals, diag, peer_cur_host[rank], peer_next_host, flags,
+                       row_offset, peer_flags_host, rank, world, epoch + 1, done_counter, err_flag, device, stream);
+    if (rc != FGK_OK) return rc;
+    const char* y_rows = reinterpret_cast<const char*>(peer_next_host[rank]) + w * row_offset;
+    FGK_CUDA(cudaMemcpyAsync(y_host, y_rows, (size_t)(w * n_rows), cudaMemcpyDeviceToHost, st));
+    FGK_CUDA(cudaStreamSynchronize(st));
+    return FGK_OK;
+}
+
 extern "C" int fgk_peer_allreduce_sum(const double* src, int64_t n, int64_t src_rows, double* dst, double* const* peer_scratch_host,
                                       int64_t slot_stride, int area, uint64_t* const* peer_flags_host, int rank,
                                       int world, uint64_t epoch, uint32_t* done_counter, uint64_t* err_flag,

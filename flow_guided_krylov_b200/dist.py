@@ -470,12 +470,31 @@ class FusedShardedOperator:
             self._host_io = (key, torch.empty(self.P.n_rows, dtype=ydt, device=self.device),
                              torch.empty(self.P.n_rows, dtype=ydt).pin_memory())
         _, xl, yh = self._host_io
-        xl.copy_(x_host[self.row_begin:self.row_end], non_blocking=True)
-        self.gather_local(xl)
-        ynew = self.step()
         dst = out if out is not None else yh
-        dst.copy_(ynew[self.row_begin:self.row_end], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        xs = x_host[self.row_begin:self.row_end]
+        if not (xs.is_contiguous() and dst.is_contiguous() and not dst.is_cuda):
+            raise ValueError("matvec_host: contiguous host tensors expected")
+        import ctypes as C
+        from . import _native as nat
+        self._cplx = x_host.is_complex()
+        flags = (nat.PEER_COMPLEX if self._cplx else 0) | (nat.PEER_PACKED_F32 if self.packed else 0)
+        if self.packed:
+            sp, pk, dg = self.P._sellf
+            a_cols, a_vals, a_diag = nat.ptr(pk), None, nat.ptr(dg, torch.float64)
+        else:
+            sp, sc, sv = self.P._sell
+            a_cols, a_vals, a_diag = nat.ptr(sc, torch.int32), nat.ptr(sv, torch.float64), None
+        nxt = 1 - self._cur
+        self._epoch += 2                          # the gather and the step
+        if (self._epoch // 2) % self.ERR_POLL == 0:
+            self.check()
+        # ONE library call: H2D of the slice, peer gather, fused step, D2H of the rows, synchronise
+        nat.check(nat.lib().fgk_peer_matvec_host(
+            self.P.n_rows, nat.ptr(sp, torch.int64), a_cols, a_vals, a_diag, C.c_void_p(xs.data_ptr()),
+            C.c_void_p(xl.data_ptr()), self._bufs[self._cur], self._bufs[nxt], C.c_void_p(dst.data_ptr()), flags,
+            self.row_begin, self._flags, self.rank, self.world, self._epoch - 1, nat.ptr(self._done),
+            nat.ptr(self._err, torch.int64), self.dev, nat.stream_ptr(self.device)))
+        self._cur = nxt
         return dst
 
     def diagonal(self):

@@ -266,6 +266,16 @@ int fgk_davidson_step(int mode, int64_t n_local, int64_t ld, int m, const double
                       const double* diag, double* t, const double* w, double* out, double* partial,
                       int n_blocks, double* nrm_out, int device, void* stream);
 
+/* Host-buffer form of the multi-GPU step (the e2e call): x_host_slice = this rank's n_rows
+ * entries of x in (pinned) host memory; copied to x_dev_slice, exchanged with fgk_peer_gather into
+ * every rank's CURRENT vector (peer_cur), one fgk_peer_step into peer_next, the rank's rows of the
+ * result copied to y_host; synchronises the stream.  Uses epochs `epoch` and `epoch + 1`. */
+int fgk_peer_matvec_host(int64_t n_rows, const int64_t* slice_ptr, const void* cols_or_packed,
+                         const double* vals, const double* diag, const void* x_host_slice, void* x_dev_slice,
+                         double* const* peer_cur, double* const* peer_next, void* y_host, int flags,
+                         int64_t row_offset, uint64_t* const* peer_flags, int rank, int world, uint64_t epoch,
+                         uint32_t* done_counter, uint64_t* err_flag, int device, void* stream);
+
 /* Small all-reduce (sum) of n <= slot_stride doubles over peer memory: the dot products of a
  * row-sharded Krylov iteration.  src holds src_rows rows of n doubles (the per-CTA partial rows of
  * fgk_davidson_step; 1 for a plain vector), added in row order first.  peer_scratch[p]: rank p's
