@@ -580,6 +580,7 @@ class MolecularHamiltonian:
                                                nat.ptr(vals, torch.float64), st))
         P = ProjectedH(n, row_ptr, cols, vals, self.device, row_begin, row_end, mode)
         P._index = idx
+        P._ham = self
         if profile:
             ev[3].record()
             ev[3].synchronize()
@@ -709,6 +710,7 @@ class MolecularHamiltonian:
         empty_v = torch.empty(0, dtype=torch.float64, device=dev)
         P = ProjectedH(n, row_ptr, empty_c, empty_v, self.device, row_begin, row_end, mode)
         P._index = idx
+        P._ham = self
         P._sellf = (slice_ptr, pk, diag)
         P._row_len = row_len
         P._diag_cache = diag

@@ -17,6 +17,27 @@ import torch
 
 DENSE_EIG_MAX = 3072
 FUSED_DAVIDSON_MIN_ROWS = 16384     # above: fused iteration kernels (fgk_davidson_step) on one GPU too
+MODEL_SPACE = 512                   # determinants (lowest diagonal) whose exact block seeds the fused Davidson
+
+
+def _model_space_start(op, diag_full, nb):
+    """Start vectors from the exact eigenvectors of the projected H inside the MODEL_SPACE
+    determinants of lowest diagonal energy (a 512 x 512 dense problem, built by the row builder on
+    that sub-basis: ~6 ms), embedded into the full space.  Unit vectors on the lowest diagonals --
+    the plain start -- needed 78 products on a 14,400-determinant test problem, this start 59-63
+    (CPU experiment with the same iteration; the preconditioner is unchanged).  None if the operator
+    does not know its Hamiltonian / basis."""
+    P = getattr(op, "P", None)
+    ham, idx = getattr(P, "_ham", None), getattr(P, "_index", None)
+    n = diag_full.shape[0]
+    if ham is None or idx is None or n < 8 * MODEL_SPACE:
+        return None, None
+    sel = torch.argsort(diag_full)[:MODEL_SPACE]
+    sub = idx.dets[sel].contiguous()
+    D = ham.projected_csr(sub, P.mode & 3, packed=True).to_dense()
+    _, U = torch.linalg.eigh(0.5 * (D + D.T))
+    return sel, U[:, :nb].contiguous()
+
 
 
 class _LocalOp:
@@ -214,11 +235,16 @@ def _davidson_fused(op, k, tol, max_iter, max_space, v0, phases):
     keep = min(max(2 * k + 2, m_max // 3), m_max - k)
     V = torch.zeros(m_max, nl, dtype=torch.float64, device=dev)
     W = torch.zeros(m_max, nl, dtype=torch.float64, device=dev)
-    start = torch.argsort(diag_full)[:nb]
     V0 = torch.zeros(n, nb, dtype=torch.float64, device=dev)
-    V0[start, torch.arange(nb, device=dev)] = 1.0
     gen = torch.Generator(device=dev).manual_seed(20240229)       # same stream on every rank
-    V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen, device=dev)
+    sel, U = _model_space_start(op, diag_full, nb)
+    if sel is not None:                                  # exact eigenvectors of the model-space block
+        V0[sel] = U
+        V0 += 1e-3 * torch.randn(n, nb, dtype=torch.float64, generator=gen, device=dev)
+    else:
+        start = torch.argsort(diag_full)[:nb]
+        V0[start, torch.arange(nb, device=dev)] = 1.0
+        V0 += 1e-2 * torch.randn(n, nb, dtype=torch.float64, generator=gen, device=dev)
     if v0 is not None:
         V0[:, 0] = v0.to(dev, torch.float64)
     V0 = V0[lo:hi].contiguous()
